@@ -1,0 +1,176 @@
+/* odeu.h - C ABI of the B200-native batched EKF-over-embedded-Runge-Kutta hot path.
+ *
+ * This is the drop-in boundary for ONE path of f-lair/ode-uncertainty: the time loop that the
+ * reference runs as `lax.scan` over jitted predict/correct closures
+ *     scripts/run_filter.py:166-224                 unroll()
+ *     scripts/run_parameter_estimation.py:685-796   nll()
+ * with the plugins it composes
+ *     src/ode/*.py                         ODE right-hand sides         -> odeu_ode_id
+ *     src/solvers/{rkf45,dopri65,bs32,heun_euler}.py  RK tableaux       -> odeu_solver_id
+ *     src/covariance_update_functions/*.py eps -> Q mappings            -> odeu_cov_fn_id
+ *     src/filters/sqrt_ekf.py:92-197,337-376  predict / correct         -> odeu_ekf_run
+ *     src/filters/particle_filter.py:73-118   perturbed-solver ensemble -> odeu_pf_run
+ *     src/utils.py:109-128                 negative_log_gaussian_sqrt   -> nll output
+ *
+ * Conventions
+ *  - plain C types only; every pointer is either HOST (small, shared configuration matrices)
+ *    or DEVICE (per-trajectory batches), as marked on each field.
+ *  - the library never allocates or retains caller memory: outputs are written in place into
+ *    caller-provided device buffers; launches are asynchronous on the given CUDA stream.
+ *  - device batch layout is component-major, trajectory-minor ("[n][B]"), so every global
+ *    access of a warp is coalesced.
+ *  - numerical failure is NOT an error: NaN/Inf propagate per trajectory like the reference
+ *    (SURVEY section 5).  Return value: 0 ok; <0 invalid argument / unsupported combination;
+ *    >0 a cudaError_t.  odeu_last_error() gives the message (thread-local).
+ *  - the covariance is exchanged as the full matrix P = P_sqrt P_sqrt^T and S = S_sqrt S_sqrt^T:
+ *    the reference's factors are defined only up to column signs (tests/test_utils.py:31
+ *    compares c @ c.T for that reason).
+ */
+#ifndef ODEU_H_
+#define ODEU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODEU_VERSION 1
+
+/* src/ode/__init__.py */
+typedef enum {
+  ODEU_ODE_LORENZ = 0,          /* src/ode/lorenz.py:30-54          n=3  p=3  */
+  ODEU_ODE_VAN_DER_POL = 1,     /* src/ode/van_der_pol.py:22-46     n=2  p=1  */
+  ODEU_ODE_LOTKA_VOLTERRA = 2,  /* src/ode/lotka_volterra.py:31-54  n=2  p=4  */
+  ODEU_ODE_PENDULUM = 3,        /* src/ode/pendulum.py:22-46        n=2  p=1  */
+  ODEU_ODE_LCAO = 4,            /* src/ode/lcao.py:35-63            n=2D p=3 (variant = D) */
+  ODEU_ODE_HODGKIN_HUXLEY = 5,  /* src/ode/hodgkin_huxley.py:61-281 variant 0 full(8) 1 reduced-1(7) 4 reduced-4(4); p=15 */
+  ODEU_ODE_MULTI_HH = 6         /* src/ode/hodgkin_huxley.py:284-439 n = num_compartments * dim(variant) */
+} odeu_ode_id;
+
+/* src/solvers/__init__.py (explicit embedded RK only; DiffraxSolverBuilder is out of scope) */
+typedef enum {
+  ODEU_SOLVER_RKF45 = 0,      /* src/solvers/rkf45.py     */
+  ODEU_SOLVER_DOPRI65 = 1,    /* src/solvers/dopri65.py   */
+  ODEU_SOLVER_BS32 = 2,       /* src/solvers/bs32.py      */
+  ODEU_SOLVER_HEUN_EULER = 3  /* src/solvers/heun_euler.py */
+} odeu_solver_id;
+
+/* src/covariance_update_functions/__init__.py */
+typedef enum {
+  ODEU_COV_DIAGONAL = 0,        /* diagonal.py:11-58        P += diag((scale*eps)^2)        */
+  ODEU_COV_OUTER = 1,           /* outer.py:11-62           P += (scale*eps)(scale*eps)^T   */
+  ODEU_COV_STATIC_DIAGONAL = 2  /* static_diagonal.py:11-48 P += scale^2 I (use_static_cov_fn) */
+} odeu_cov_fn_id;
+
+/* Plugin selection = what jsonargparse instantiates from class_path/init_args
+ * (scripts/run_filter.py:31-47). */
+typedef struct {
+  int32_t ode_id;              /* odeu_ode_id */
+  int32_t ode_variant;         /* HH model (0/1/4), LCAO D; else 0 */
+  int32_t num_compartments;    /* ODEU_ODE_MULTI_HH only; else 0 */
+  int32_t solver_id;           /* odeu_solver_id */
+  double step_size;            /* SolverBuilder(step_size), src/solvers/solver.py:18-26 */
+  int32_t cov_fn_id;           /* odeu_cov_fn_id */
+  double cov_scale;            /* DiagonalCovarianceUpdate(scale) / static scale */
+  int32_t disable_cov_update;  /* SQRT_EKF(disable_cov_update), src/filters/sqrt_ekf.py:36-43 */
+} odeu_plan_desc;
+
+typedef struct odeu_plan odeu_plan; /* opaque; immutable after creation; re-entrant per stream */
+
+int odeu_plan_create(const odeu_plan_desc* desc, odeu_plan** out);
+void odeu_plan_destroy(odeu_plan* plan);
+/* flattened state dimension n = N*D and number of scalar parameters of the plan's ODE */
+int odeu_plan_state_dim(const odeu_plan* plan);
+int odeu_plan_num_params(const odeu_plan* plan);
+/* reference default parameter values, flat, in ODEBuilder.params order (HOST out[num_params]) */
+int odeu_plan_default_params(const odeu_plan* plan, double* out);
+
+/* One batched EKF run = unroll()/nll() for B independent trajectories. */
+typedef struct {
+  int64_t B;                 /* trajectories / parameter sets */
+  int64_t T;                 /* steps, = ceil((tN - t0) / h), scripts/run_filter.py:95 */
+  double t0;
+  int32_t L;                 /* observation dimension, 0 = prediction only (run_filter.py:114-121) */
+  /* ---- inputs */
+  const double* x0;          /* DEVICE [n][B] */
+  const double* P0;          /* DEVICE [n*n][B] full covariance per trajectory, or NULL */
+  const double* P0_sqrt;     /* HOST   [n][n] shared factor (used when P0 == NULL) */
+  const double* theta;       /* DEVICE [p][B] per-trajectory parameters, or NULL = defaults / theta_shared */
+  const double* theta_shared;/* HOST   [p] or NULL = reference defaults */
+  const double* Q_sqrt;      /* HOST   [n][n] or NULL (= 0), state["Q_sqrt"], sqrt_ekf.py:77 */
+  double gamma_sqrt;         /* state["gamma_sqrt"], sqrt_ekf.py:78 */
+  const double* H;           /* HOST   [L][n] measurement matrix */
+  const double* R_sqrt;      /* HOST   [L][L] */
+  const double* ys;          /* DEVICE [T_obs][L] shared, or [T_obs][L][B] when ys_per_trajectory */
+  int32_t ys_per_trajectory;
+  const uint8_t* correct_flags;   /* DEVICE [T]  run_filter.py:102-103 */
+  const int64_t* xy_index_map;    /* DEVICE [T]  run_filter.py:104-105 */
+  int64_t save_interval;     /* 0 = no trajectory output; else slots 0, s, 2s, ... (run_filter.py:219-222) */
+  /* ---- outputs (DEVICE, any may be NULL) */
+  double* xT;                /* [n][B]    final mean */
+  double* epsT;              /* [n][B]    last local error estimate */
+  double* PT;                /* [n*n][B]  final covariance */
+  double* yhatT;             /* [L][B]    last pre-update H x */
+  double* ST;                /* [L*L][B]  last innovation covariance */
+  double* nll;               /* [B]       sum over observation steps of negative_log_gaussian_sqrt */
+  double* tT;                /* [1]       final time (accumulated t + h) */
+  double* out_t;             /* [T_save]            T_save = T / save_interval + 1 */
+  double* out_x;             /* [T_save][n][B] */
+  double* out_eps;           /* [T_save][n][B] */
+  double* out_P;             /* [T_save][n*n][B] */
+  double* out_yhat;          /* [T_save][L][B] */
+  double* out_S;             /* [T_save][L*L][B] */
+} odeu_ekf_io;
+
+/* Replaces unroll() (scripts/run_filter.py:166-224) and the scan of nll()
+ * (scripts/run_parameter_estimation.py:771-794).  `cuda_stream` is a cudaStream_t. */
+int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream);
+
+/* Perturbed-solver particle ensemble (src/filters/particle_filter.py:24-118; Conrad et al.
+ * baseline): M independent RK steps, after each step x += p with p ~ N(0, covfn(0, eps_m));
+ * the particle with GLOBAL index 0 is noise-free (:104-105).  The reference draws from JAX's
+ * threefry stream (sample-level parity impossible); here the normals come from
+ * Philox4x32-10 keyed by `seed` with counter (global particle index, global step index), so
+ * results do not depend on how particles are sharded over GPUs or on chunked (resumed) runs. */
+typedef struct {
+  int64_t M;                 /* particles on this rank */
+  int64_t T;                 /* steps */
+  double t0;
+  const double* x0;          /* DEVICE [n][M], or NULL -> x0_shared */
+  const double* x0_shared;   /* HOST   [n] (ParticleFilter.init_state broadcasts x0, :52-63) */
+  const double* theta_shared;/* HOST   [p] or NULL = reference defaults */
+  uint64_t seed;
+  int64_t particle_offset;   /* global index of local particle 0 (sharding) */
+  int64_t step_offset;       /* global index of local step 0 (resume) */
+  int64_t save_interval;     /* 0 = none */
+  double* xT;                /* DEVICE [n][M] */
+  double* epsT;              /* DEVICE [n][M] */
+  double* tT;                /* DEVICE [1] */
+  double* out_t;             /* DEVICE [T_save] */
+  double* out_x;             /* DEVICE [T_save][n][M] */
+  double* out_eps;           /* DEVICE [T_save][n][M] */
+} odeu_pf_io;
+
+/* Replaces unroll() driven by ParticleFilter.build_predict (particle_filter.py:73-118). */
+int odeu_pf_run(const odeu_plan* plan, const odeu_pf_io* io, void* cuda_stream);
+
+/* FP64-pipe micro-benchmark (roofline denominator for the EKF kernels): launches `blocks` x
+ * `threads` threads each running 8 independent chains of `iters` dependent DFMAs; writes the
+ * number of flops issued to *flops_out (HOST).  Time it with CUDA events on `cuda_stream`. */
+int odeu_bench_dfma(int64_t iters, int32_t blocks, int32_t threads, double* scratch_dev,
+                    double* flops_out, void* cuda_stream);
+
+/* number of kernel launches issued by this library in this process (bench bookkeeping) */
+int64_t odeu_launch_count(void);
+
+/* last error message of the calling thread; returns the message length */
+size_t odeu_last_error(char* buf, size_t buflen);
+
+int odeu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODEU_H_ */

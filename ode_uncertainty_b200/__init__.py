@@ -1,0 +1,10 @@
+"""B200-native batched EKF-over-embedded-Runge-Kutta path of f-lair/ode-uncertainty.
+
+Hand-written sm_100a CUDA behind a C ABI (include/odeu.h, libodeu.so); Python only marshals
+buffers.  No CPU fallback: the CUDA library must be built (`make`) and inputs must be CUDA
+tensors.
+"""
+from . import _native
+from .engine import EkfResult, PfResult, Plan, ekf_run, launch_count, pf_run
+
+__all__ = ["Plan", "ekf_run", "pf_run", "EkfResult", "PfResult", "launch_count", "_native"]

@@ -1,0 +1,190 @@
+// Whole-trajectory EKF kernel, one thread per trajectory (small states: everything in registers).
+//
+// Replaces the reference's time loop `lax.scan(scan_wrapper, ...)` (scripts/run_filter.py:204-217)
+// and `lax.scan(nll_step, ...)` (scripts/run_parameter_estimation.py:782-794) for a batch of B
+// independent trajectories / parameter sets: T steps run inside ONE launch, the state never
+// leaves registers, and only the strided saves (save_interval) and the final state touch HBM.
+//
+// HBM layout (all float64, batch index fastest so every access is coalesced across a warp):
+//   x0      [n][B]          P0      [n*n][B] (optional, else shared P0 in the arguments)
+//   theta   [NP][B]         ys      [T_obs][L] shared or [T_obs][L][B] per trajectory
+//   out_x   [T_save][n][B]  out_eps [T_save][n][B]   out_P [T_save][n*n][B]
+//   out_yhat[T_save][L][B]  out_S   [T_save][L*L][B] out_t [T_save]
+//   xT [n][B]  epsT [n][B]  PT [n*n][B]  yhatT [L][B]  ST [L*L][B]  nll [B]  tT [1]
+#pragma once
+#include "ekf_core.cuh"
+
+namespace odeu {
+
+template <int NX, int NP>
+struct EkfArgs {
+  long long B;
+  long long T;
+  double t0, h;
+  int L;
+  int noise_mode, cov_fn;
+  double cov_scale;
+  long long save_interval;  // 0: no trajectory output
+  int ys_per_traj;
+  int has_obs;
+  // device pointers
+  const double* x0;
+  const double* P0;       // nullable
+  const double* theta;    // nullable -> theta_shared
+  const double* ys;       // nullable when has_obs == 0
+  const unsigned char* flags;
+  const long long* ymap;
+  double* xT; double* epsT; double* PT; double* yhatT; double* ST; double* nll; double* tT;
+  double* out_t; double* out_x; double* out_eps; double* out_P; double* out_yhat; double* out_S;
+  // small shared matrices, by value (constant bank)
+  double P0s[NX * NX];
+  double GQ[NX * NX];     // gamma * Q_sqrt Q_sqrt^T
+  double H[NX * NX];      // [L][n]
+  double R[NX * NX];      // [L][L] = R_sqrt R_sqrt^T
+  double theta_shared[NP];
+};
+
+template <int n>
+ODEU_HD void save_slot(long long slot, long long B, long long b, int L,
+                                          const double* x, const double* eps,
+                                          const double (*P)[n], const double* yhat,
+                                          const double (*Smat)[n], double* out_x, double* out_eps,
+                                          double* out_P, double* out_yhat, double* out_S) {
+  constexpr int U = (n <= 4) ? n : 1;
+#pragma unroll U
+  for (int i = 0; i < n; ++i) {
+    if (out_x) out_x[(slot * n + i) * B + b] = x[i];
+    if (out_eps) out_eps[(slot * n + i) * B + b] = eps[i];
+  }
+  if (out_P) {
+#pragma unroll U
+    for (int i = 0; i < n; ++i)
+#pragma unroll U
+      for (int j = 0; j < n; ++j) out_P[(slot * n * n + i * n + j) * B + b] = P[i][j];
+  }
+#pragma unroll U
+  for (int l = 0; l < n; ++l) {
+    if (l < L) {
+      if (out_yhat) out_yhat[(slot * L + l) * B + b] = yhat[l];
+      if (out_S) {
+#pragma unroll U
+        for (int m = 0; m < n; ++m)
+          if (m < L) out_S[(slot * L * L + l * L + m) * B + b] = Smat[l][m];
+      }
+    }
+  }
+}
+
+// The whole life of trajectory `b`.  __host__ __device__ so the identical source can be
+// exercised on the CPU by the test-only host emulation (tests/host_emu.cu); the product only
+// ever calls it from the kernel below.
+template <class Ode, class Tab, int KC>
+ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long b) {
+  constexpr int n = Ode::NX;
+  constexpr int NP = Ode::NP;
+  constexpr int U = (n <= 4) ? n : 1;
+  const long long B = a.B;
+  const int L = a.L;
+
+  double x[n], eps[n], P[n][n], yhat[n], Smat[n][n], th[NP];
+#pragma unroll U
+  for (int i = 0; i < n; ++i) { x[i] = a.x0[i * B + b]; eps[i] = 0.0; yhat[i] = 0.0; }
+#pragma unroll U
+  for (int i = 0; i < n; ++i)
+#pragma unroll U
+    for (int j = 0; j < n; ++j) {
+      P[i][j] = a.P0 ? a.P0[(i * n + j) * B + b] : a.P0s[i * n + j];
+      Smat[i][j] = 0.0;
+    }
+#pragma unroll
+  for (int k = 0; k < NP; ++k) th[k] = a.theta ? a.theta[k * B + b] : a.theta_shared[k];
+
+  double t = a.t0;
+  double nll = 0.0;
+  const double h = a.h;
+  const long long si = a.save_interval;
+  if (si > 0) {
+    save_slot<n>(0, B, b, L, x, eps, P, yhat, Smat, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+    if (b == 0 && a.out_t) a.out_t[0] = t;
+  }
+  long long next_save = si;  // step count at which the next slot is written
+  long long slot = 1;
+
+  for (long long step = 0; step < a.T; ++step) {
+    // ---- predict (src/filters/sqrt_ekf.py:92-197)
+    double xn[n], J[n][n];
+    if constexpr (KC == n) {
+      rk_step_tangent<Ode, Tab, KC>(t, h, x, th, 0, true, xn, eps, J);
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < n; c0 += KC) {
+        double Jc[n][KC];
+        rk_step_tangent<Ode, Tab, KC>(t, h, x, th, c0, c0 == 0, xn, eps, Jc);
+#pragma unroll 1
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+          for (int k = 0; k < KC; ++k)
+            if (c0 + k < n) J[i][c0 + k] = Jc[i][k];
+      }
+    }
+    propagate_cov<n>(J, P);
+    add_process_noise<n>(a.noise_mode, a.cov_fn, a.cov_scale, eps, a.GQ, P);
+#pragma unroll U
+    for (int i = 0; i < n; ++i) x[i] = xn[i];
+    t = t + h;  // accumulated like rksolver.py:145 (stage times depend on it)
+
+    // ---- correct + log-likelihood (src/filters/sqrt_ekf.py:337-376, src/utils.py:109-128)
+    if (a.has_obs && a.flags[step]) {
+      const long long oi = a.ymap[step];
+      double y[n];
+#pragma unroll U
+      for (int l = 0; l < n; ++l)
+        if (l < L) y[l] = a.ys_per_traj ? a.ys[(oi * L + l) * B + b] : a.ys[oi * L + l];
+      nll += correct_step<n>(L, a.H, a.R, y, x, P, yhat, Smat);
+    }
+
+    // ---- strided save (scripts/run_filter.py:219-222)
+    if (si > 0 && step + 1 == next_save) {
+      save_slot<n>(slot, B, b, L, x, eps, P, yhat, Smat, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+      if (b == 0 && a.out_t) a.out_t[slot] = t;
+      ++slot;
+      next_save += si;
+    }
+  }
+
+  // ---- final state
+#pragma unroll U
+  for (int i = 0; i < n; ++i) {
+    if (a.xT) a.xT[i * B + b] = x[i];
+    if (a.epsT) a.epsT[i * B + b] = eps[i];
+  }
+  if (a.PT) {
+#pragma unroll U
+    for (int i = 0; i < n; ++i)
+#pragma unroll U
+      for (int j = 0; j < n; ++j) a.PT[(i * n + j) * B + b] = P[i][j];
+  }
+#pragma unroll U
+  for (int l = 0; l < n; ++l) {
+    if (l < L) {
+      if (a.yhatT) a.yhatT[l * B + b] = yhat[l];
+      if (a.ST) {
+#pragma unroll U
+        for (int m = 0; m < n; ++m)
+          if (m < L) a.ST[(l * L + m) * B + b] = Smat[l][m];
+      }
+    }
+  }
+  if (a.nll) a.nll[b] = nll;
+  if (b == 0 && a.tT) a.tT[0] = t;
+}
+
+template <class Ode, class Tab, int KC, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+ekf_thread_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a) {
+  const long long b = (long long)blockIdx.x * BLOCK + threadIdx.x;
+  if (b >= a.B) return;
+  ekf_trajectory<Ode, Tab, KC>(a, b);
+}
+
+}  // namespace odeu

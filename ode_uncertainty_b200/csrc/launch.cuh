@@ -1,0 +1,145 @@
+// Host launcher template: validates an odeu_ekf_io, folds the small shared matrices into the
+// by-value kernel arguments and launches the whole-trajectory kernel on the caller's stream.
+#pragma once
+#include "ekf_thread.cuh"
+#include "pf_thread.cuh"
+#include "plan.h"
+
+namespace odeu {
+
+// per-ODE launch shape: BLOCK threads, MINB resident blocks per SM (register cap), KC tangent
+// columns carried per RK pass
+template <class Ode>
+struct LaunchCfg {
+  static constexpr int BLOCK = 64;
+  static constexpr int MINB = (Ode::NX <= 4) ? 8 : 2;
+  static constexpr int KC = (Ode::NX <= 4) ? Ode::NX : 1;
+};
+
+// Validates `io` and folds the shared host matrices into the by-value kernel arguments.
+template <class Ode>
+int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX, Ode::NP>& a) {
+  constexpr int n = Ode::NX;
+  constexpr int NP = Ode::NP;
+  if (io.B <= 0 || io.T < 0) { set_error("odeu_ekf_run: B must be > 0 and T >= 0"); return -1; }
+  if (io.L < 0 || io.L > n) { set_error("odeu_ekf_run: L=%d outside [0, n=%d]", io.L, n); return -1; }
+  if (!io.x0) { set_error("odeu_ekf_run: x0 is required"); return -1; }
+  if (!io.P0 && !io.P0_sqrt) { set_error("odeu_ekf_run: P0 or P0_sqrt is required"); return -1; }
+  if (io.save_interval < 0) { set_error("odeu_ekf_run: save_interval < 0"); return -1; }
+  if (io.L > 0 && (!io.H || !io.R_sqrt || !io.ys || !io.correct_flags || !io.xy_index_map)) {
+    set_error("odeu_ekf_run: L > 0 needs H, R_sqrt, ys, correct_flags, xy_index_map");
+    return -1;
+  }
+
+  a.B = io.B; a.T = io.T; a.t0 = io.t0; a.h = plan.desc.step_size; a.L = io.L;
+  a.cov_fn = plan.desc.cov_fn_id; a.cov_scale = plan.desc.cov_scale;
+  a.save_interval = io.save_interval;
+  a.ys_per_traj = io.ys_per_trajectory; a.has_obs = io.L > 0 ? 1 : 0;
+  a.x0 = io.x0; a.P0 = io.P0; a.theta = io.theta; a.ys = io.ys;
+  a.flags = io.correct_flags; a.ymap = (const long long*)io.xy_index_map;
+  a.xT = io.xT; a.epsT = io.epsT; a.PT = io.PT; a.yhatT = io.yhatT; a.ST = io.ST; a.nll = io.nll;
+  a.tT = io.tT;
+  a.out_t = io.out_t; a.out_x = io.out_x; a.out_eps = io.out_eps; a.out_P = io.out_P;
+  a.out_yhat = io.out_yhat; a.out_S = io.out_S;
+
+  // P0 = P0_sqrt P0_sqrt^T (scripts/run_filter.py:74-78 builds the factor)
+  for (int i = 0; i < n * n; ++i) { a.P0s[i] = 0.0; a.GQ[i] = 0.0; a.H[i] = 0.0; a.R[i] = 0.0; }
+  if (io.P0_sqrt)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s += io.P0_sqrt[i * n + k] * io.P0_sqrt[j * n + k];
+        a.P0s[i * n + j] = s;
+      }
+  // Qany = any(Q_sqrt >= 1e-16) (sqrt_ekf.py:108,128); GQ = (g Q_sqrt)(g Q_sqrt)^T
+  bool qany = false;
+  if (io.Q_sqrt) {
+    for (int i = 0; i < n * n; ++i) qany = qany || (io.Q_sqrt[i] >= 1e-16);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k)
+          s += (io.gamma_sqrt * io.Q_sqrt[i * n + k]) * (io.gamma_sqrt * io.Q_sqrt[j * n + k]);
+        a.GQ[i * n + j] = s;
+      }
+  }
+  a.noise_mode = plan.desc.disable_cov_update ? (qany ? NOISE_Q_ONLY : NOISE_NONE)
+                                              : (qany ? NOISE_EPS_PLUS_Q : NOISE_COVFN);
+  const int L = io.L;
+  for (int l = 0; l < L; ++l) {
+    for (int j = 0; j < n; ++j) a.H[l * n + j] = io.H[l * n + j];
+    for (int m = 0; m < L; ++m) {
+      double s = 0.0;
+      for (int k = 0; k < L; ++k) s += io.R_sqrt[l * L + k] * io.R_sqrt[m * L + k];
+      a.R[l * L + m] = s;
+    }
+  }
+  for (int k = 0; k < NP; ++k)
+    a.theta_shared[k] = io.theta_shared ? io.theta_shared[k] : plan.theta_default[k];
+  return 0;
+}
+
+template <class Ode, class Tab>
+int launch_ekf(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream) {
+  using Cfg = LaunchCfg<Ode>;
+  EkfArgs<Ode::NX, Ode::NP> a;
+  if (int rc = fill_ekf_args<Ode>(plan, io, a)) return rc;
+  const long long grid = (io.B + Cfg::BLOCK - 1) / Cfg::BLOCK;
+  ekf_thread_kernel<Ode, Tab, Cfg::KC, Cfg::BLOCK, Cfg::MINB>
+      <<<(unsigned)grid, Cfg::BLOCK, 0, stream>>>(a);
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error("odeu_ekf_run: launch failed: %s", cudaGetErrorString(err));
+    return (int)err;
+  }
+  return 0;
+}
+
+template <class Ode>
+int fill_pf_args(const odeu_plan& plan, const odeu_pf_io& io, PfArgs<Ode::NX, Ode::NP>& a) {
+  constexpr int n = Ode::NX;
+  constexpr int NP = Ode::NP;
+  if (io.M <= 0 || io.T < 0) { set_error("odeu_pf_run: M must be > 0 and T >= 0"); return -1; }
+  if (!io.x0 && !io.x0_shared) { set_error("odeu_pf_run: x0 or x0_shared is required"); return -1; }
+  if (io.save_interval < 0) { set_error("odeu_pf_run: save_interval < 0"); return -1; }
+  a.M = io.M; a.T = io.T; a.t0 = io.t0; a.h = plan.desc.step_size;
+  a.cov_fn = plan.desc.cov_fn_id; a.cov_scale = plan.desc.cov_scale;
+  a.seed = io.seed; a.particle_offset = io.particle_offset; a.step_offset = io.step_offset;
+  a.save_interval = io.save_interval;
+  a.x0 = io.x0; a.xT = io.xT; a.epsT = io.epsT; a.tT = io.tT;
+  a.out_t = io.out_t; a.out_x = io.out_x; a.out_eps = io.out_eps;
+  for (int i = 0; i < n; ++i) a.x0s[i] = io.x0_shared ? io.x0_shared[i] : 0.0;
+  for (int k = 0; k < NP; ++k)
+    a.theta_shared[k] = io.theta_shared ? io.theta_shared[k] : plan.theta_default[k];
+  return 0;
+}
+
+template <class Ode, class Tab>
+int launch_pf(const odeu_plan& plan, const odeu_pf_io& io, cudaStream_t stream) {
+  constexpr int BLOCK = 128;
+  PfArgs<Ode::NX, Ode::NP> a;
+  if (int rc = fill_pf_args<Ode>(plan, io, a)) return rc;
+  const long long grid = (io.M + BLOCK - 1) / BLOCK;
+  pf_thread_kernel<Ode, Tab, BLOCK><<<(unsigned)grid, BLOCK, 0, stream>>>(a);
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error("odeu_pf_run: launch failed: %s", cudaGetErrorString(err));
+    return (int)err;
+  }
+  return 0;
+}
+
+template <class Ode>
+Launchers resolve_solver(int solver) {
+  switch (solver) {
+    case ODEU_SOLVER_RKF45: return {&launch_ekf<Ode, TabRKF45>, &launch_pf<Ode, TabRKF45>};
+    case ODEU_SOLVER_DOPRI65: return {&launch_ekf<Ode, TabDopri65>, &launch_pf<Ode, TabDopri65>};
+    case ODEU_SOLVER_BS32: return {&launch_ekf<Ode, TabBS32>, &launch_pf<Ode, TabBS32>};
+    case ODEU_SOLVER_HEUN_EULER: return {&launch_ekf<Ode, TabHeunEuler>, &launch_pf<Ode, TabHeunEuler>};
+    default: return {nullptr, nullptr};
+  }
+}
+
+}  // namespace odeu

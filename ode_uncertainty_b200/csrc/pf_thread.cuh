@@ -1,0 +1,148 @@
+// Perturbed-solver particle ensemble, one thread per particle
+// (reference: src/filters/particle_filter.py:73-118).
+//
+// Per step: plain RK step, then x += p, p ~ N(0, covfn(0, eps)) with
+//   Diagonal : cov = diag((scale eps)^2)        -> p_i = scale eps_i z_i      (diagonal.py:24-41)
+//   Outer    : cov = (scale eps)(scale eps)^T   -> p   = scale eps z          (outer.py:24-42)
+//   Static   : cov = scale^2 I                  -> p_i = scale z_i            (static_diagonal.py:14-29)
+// (the reference factorises the dense [M,n,n] covariance by SVD, particle_filter.py:93-102; for
+// these three plugins the factor is known in closed form).  Global particle 0 stays noise-free.
+// Normals: Philox4x32-10, key = seed, counter = (global particle, global step, draw, 0),
+// Box-Muller on 2 x 53-bit... (32-bit pairs) uniforms.
+#pragma once
+#include "ekf_core.cuh"
+
+namespace odeu {
+
+struct Philox {
+  static constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void round(unsigned (&c)[4], unsigned k0, unsigned k1) {
+    const unsigned long long p0 = (unsigned long long)M0 * c[0];
+    const unsigned long long p1 = (unsigned long long)M1 * c[2];
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c[1] ^ k0;
+    const unsigned n1 = (unsigned)p1;
+    const unsigned n2 = (unsigned)(p0 >> 32) ^ c[3] ^ k1;
+    const unsigned n3 = (unsigned)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __host__ __device__ static inline void gen(unsigned long long seed, unsigned long long particle,
+                                             unsigned long long step, unsigned draw,
+                                             unsigned (&out)[4]) {
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+    // counter: particle (40 bits) | step (48 bits) | draw (8 bits) spread over 128 bits
+    unsigned c[4] = {(unsigned)particle, (unsigned)(particle >> 32) | (draw << 24),
+                     (unsigned)step, (unsigned)(step >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round(c, k0, k1);
+      k0 += W0; k1 += W1;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+  // two standard normals from one 128-bit block (Box-Muller; u1 in (0,1], u2 in [0,1))
+  __host__ __device__ static inline void normal2(unsigned long long seed, unsigned long long particle,
+                                                 unsigned long long step, unsigned draw,
+                                                 double* z0, double* z1) {
+    unsigned r[4];
+    gen(seed, particle, step, draw, r);
+    const double u1 = ((double)(((unsigned long long)r[0] << 21) ^ (r[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+    const double u2 = (double)(((unsigned long long)r[2] << 21) ^ (r[3] >> 11)) * (1.0 / 9007199254740992.0);
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    *z0 = rad * c;
+    *z1 = rad * s;
+  }
+};
+
+template <int NX, int NP>
+struct PfArgs {
+  long long M, T;
+  double t0, h;
+  int cov_fn;
+  double cov_scale;
+  unsigned long long seed;
+  long long particle_offset, step_offset, save_interval;
+  const double* x0;
+  double* xT; double* epsT; double* tT; double* out_t; double* out_x; double* out_eps;
+  double x0s[NX];
+  double theta_shared[NP];
+};
+
+template <class Ode, class Tab>
+ODEU_HD void pf_particle(const PfArgs<Ode::NX, Ode::NP>& a, const long long m) {
+  constexpr int n = Ode::NX;
+  constexpr int NP = Ode::NP;
+  const long long M = a.M;
+  const unsigned long long gid = (unsigned long long)(a.particle_offset + m);
+  double x[n], eps[n], th[NP];
+#pragma unroll
+  for (int i = 0; i < n; ++i) { x[i] = a.x0 ? a.x0[i * M + m] : a.x0s[i]; eps[i] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < NP; ++k) th[k] = a.theta_shared[k];
+  double t = a.t0;
+  const long long si = a.save_interval;
+  if (si > 0) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      if (a.out_x) a.out_x[i * M + m] = x[i];
+      if (a.out_eps) a.out_eps[i * M + m] = 0.0;
+    }
+    if (m == 0 && a.out_t) a.out_t[0] = t;
+  }
+  long long next_save = si, slot = 1;
+  for (long long step = 0; step < a.T; ++step) {
+    double xn[n];
+    rk_step_plain<Ode, Tab>(t, a.h, x, th, xn, eps);
+    t = t + a.h;
+    if (gid != 0) {
+      const unsigned long long gstep = (unsigned long long)(a.step_offset + step);
+      if (a.cov_fn == COV_OUTER) {
+        double z0, z1;
+        Philox::normal2(a.seed, gid, gstep, 0, &z0, &z1);
+#pragma unroll
+        for (int i = 0; i < n; ++i) xn[i] = fma(a.cov_scale * eps[i], z0, xn[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < n; i += 2) {
+          double z0, z1;
+          Philox::normal2(a.seed, gid, gstep, (unsigned)(i / 2), &z0, &z1);
+          const double s0 = (a.cov_fn == COV_DIAGONAL) ? a.cov_scale * eps[i] : a.cov_scale;
+          xn[i] = fma(s0, z0, xn[i]);
+          if (i + 1 < n) {
+            const double s1 = (a.cov_fn == COV_DIAGONAL) ? a.cov_scale * eps[i + 1] : a.cov_scale;
+            xn[i + 1] = fma(s1, z1, xn[i + 1]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xn[i];
+    if (si > 0 && step + 1 == next_save) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        if (a.out_x) a.out_x[(slot * n + i) * M + m] = x[i];
+        if (a.out_eps) a.out_eps[(slot * n + i) * M + m] = eps[i];
+      }
+      if (m == 0 && a.out_t) a.out_t[slot] = t;
+      ++slot;
+      next_save += si;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    if (a.xT) a.xT[i * M + m] = x[i];
+    if (a.epsT) a.epsT[i * M + m] = eps[i];
+  }
+  if (m == 0 && a.tT) a.tT[0] = t;
+}
+
+template <class Ode, class Tab, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+pf_thread_kernel(const __grid_constant__ PfArgs<Ode::NX, Ode::NP> a) {
+  const long long m = (long long)blockIdx.x * BLOCK + threadIdx.x;
+  if (m >= a.M) return;
+  pf_particle<Ode, Tab>(a, m);
+}
+
+}  // namespace odeu

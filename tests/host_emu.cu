@@ -1,0 +1,77 @@
+// TEST INFRASTRUCTURE ONLY (never linked into libodeu.so, never on the product path).
+//
+// Compiles the *same* per-trajectory source the CUDA kernels run (ekf_trajectory / pf_particle,
+// __host__ __device__) for the CPU, so the `-m "not gpu"` suite can check the kernel arithmetic
+// against the oracle in a container without a GPU.  All pointers of the io structs are HOST
+// pointers here.  The shipped library has no such entry point.
+#include "../ode_uncertainty_b200/csrc/launch.cuh"
+
+namespace odeu {
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_err = buf;
+}
+void count_launch() {}
+
+template <class Ode, class Tab>
+int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
+  EkfArgs<Ode::NX, Ode::NP> a;
+  if (int rc = fill_ekf_args<Ode>(plan, io, a)) return rc;
+  for (long long b = 0; b < io.B; ++b) ekf_trajectory<Ode, Tab, LaunchCfg<Ode>::KC>(a, b);
+  return 0;
+}
+template <class Ode, class Tab>
+int emu_pf(const odeu_plan& plan, const odeu_pf_io& io) {
+  PfArgs<Ode::NX, Ode::NP> a;
+  if (int rc = fill_pf_args<Ode>(plan, io, a)) return rc;
+  for (long long m = 0; m < io.M; ++m) pf_particle<Ode, Tab>(a, m);
+  return 0;
+}
+
+template <class Ode>
+int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p) {
+  switch (plan.desc.solver_id) {
+    case ODEU_SOLVER_RKF45: return e ? emu_ekf<Ode, TabRKF45>(plan, *e) : emu_pf<Ode, TabRKF45>(plan, *p);
+    case ODEU_SOLVER_DOPRI65: return e ? emu_ekf<Ode, TabDopri65>(plan, *e) : emu_pf<Ode, TabDopri65>(plan, *p);
+    case ODEU_SOLVER_BS32: return e ? emu_ekf<Ode, TabBS32>(plan, *e) : emu_pf<Ode, TabBS32>(plan, *p);
+    case ODEU_SOLVER_HEUN_EULER: return e ? emu_ekf<Ode, TabHeunEuler>(plan, *e) : emu_pf<Ode, TabHeunEuler>(plan, *p);
+  }
+  return -2;
+}
+
+static int emu_dispatch(const odeu_plan_desc& d, const double* theta_default, int p,
+                        const odeu_ekf_io* e, const odeu_pf_io* pf) {
+  odeu_plan plan;
+  plan.desc = d;
+  plan.theta_default.assign(theta_default, theta_default + p);
+  switch (d.ode_id) {
+    case ODEU_ODE_LORENZ: return emu_solver<OdeLorenz>(plan, e, pf);
+    case ODEU_ODE_VAN_DER_POL: return emu_solver<OdeVanDerPol>(plan, e, pf);
+    case ODEU_ODE_LOTKA_VOLTERRA: return emu_solver<OdeLotkaVolterra>(plan, e, pf);
+    case ODEU_ODE_PENDULUM: return emu_solver<OdePendulum>(plan, e, pf);
+    case ODEU_ODE_LCAO: if (d.ode_variant == 2) return emu_solver<OdeLCAO<2>>(plan, e, pf); break;
+    case ODEU_ODE_HODGKIN_HUXLEY:
+      if (d.ode_variant == 0) return emu_solver<OdeHodgkinHuxley<0>>(plan, e, pf);
+      if (d.ode_variant == 1) return emu_solver<OdeHodgkinHuxley<1>>(plan, e, pf);
+      if (d.ode_variant == 4) return emu_solver<OdeHodgkinHuxley<4>>(plan, e, pf);
+      break;
+    case ODEU_ODE_MULTI_HH:
+      if (d.num_compartments == 2 && d.ode_variant == 1) return emu_solver<OdeMultiHH<1, 2>>(plan, e, pf);
+      if (d.num_compartments == 2 && d.ode_variant == 4) return emu_solver<OdeMultiHH<4, 2>>(plan, e, pf);
+      break;
+  }
+  return -2;
+}
+}  // namespace odeu
+
+extern "C" {
+int hostemu_ekf_run(const odeu_plan_desc* d, const double* theta_default, int p, const odeu_ekf_io* io) {
+  return odeu::emu_dispatch(*d, theta_default, p, io, nullptr);
+}
+int hostemu_pf_run(const odeu_plan_desc* d, const double* theta_default, int p, const odeu_pf_io* io) {
+  return odeu::emu_dispatch(*d, theta_default, p, nullptr, io);
+}
+const char* hostemu_last_error() { return odeu::g_err.c_str(); }
+}

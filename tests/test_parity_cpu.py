@@ -1,0 +1,112 @@
+"""CPU suite: the kernel SOURCE (ekf_trajectory, compiled for the host by tests/host_emu.cu)
+against Oracle-A golden vectors.  No GPU needed; the product path itself is covered by
+tests/test_parity_gpu.py through the C ABI."""
+import numpy as np
+import pytest
+
+import cases
+
+FAST = ["c1_lorenz_rkf45_predict", "lorenz_rkf45_obs_full", "lorenz_dopri65_obs_partial",
+        "lorenz_bs32_outer", "lorenz_heun_static", "vdp_rkf45_obs", "vdp_dopri65_predict",
+        "lv_rkf45_temper_q_only", "lv_rkf45_temper_eps_plus_q", "lv_bs32_gamma0_final_stage",
+        "lv_heun_none", "pendulum_rkf45_obs", "lcao_rkf45_obs", "hh_r4_rkf45_temper",
+        "hh_r1_rkf45_temper", "hh_full_rkf45_small_h", "c3_mhh_r1_rkf45_temper"]
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_kernel_source_matches_oracle_golden(name):
+    spec = cases.CASES[name]
+    gold = cases.load_golden(name)
+    out = cases.run_product("hostemu", spec, save_interval=1, batch=2)
+    cases.compare(out, gold, spec, b=0)
+    cases.compare(out, gold, spec, b=1)
+
+
+def test_save_interval_strides_like_reference():
+    # scripts/run_filter.py:219-222: concat(initial, states)[::save_interval]
+    spec = cases.CASES["lorenz_rkf45_obs_full"]
+    full = cases.run_product("hostemu", spec, save_interval=1)
+    strided = cases.run_product("hostemu", spec, save_interval=7)
+    for k in ("t", "x", "eps", "P", "y_hat", "S"):
+        np.testing.assert_array_equal(strided["traj"][k], full["traj"][k][::7])
+    none = cases.run_product("hostemu", spec, save_interval=0)
+    assert none["traj"] is None
+    np.testing.assert_array_equal(none["xT"], full["xT"])
+    np.testing.assert_array_equal(none["nll"], full["nll"])
+
+
+def test_resume_from_saved_state_is_bitwise():
+    """Checkpoint/resume: running T1 then T2 steps from the returned (t, x, P) equals T1+T2."""
+    import util as U
+    spec = cases.CASES["lorenz_rkf45_obs_full"]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    kw = dict(Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5, H=m["H"].numpy(),
+              R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy())
+    x0 = m["x0"].reshape(1, -1).numpy()
+    T, T1 = m["T"], 60
+    whole = U.run_ekf("hostemu", plan, x0, T, t0=m["t0"], P0_sqrt=m["P0s"].numpy(),
+                      correct_flags=m["flags"], xy_index_map=m["ymap"], **kw)
+    a = U.run_ekf("hostemu", plan, x0, T1, t0=m["t0"], P0_sqrt=m["P0s"].numpy(),
+                  correct_flags=m["flags"], xy_index_map=m["ymap"], **kw)
+    b = U.run_ekf("hostemu", plan, a["xT"], T - T1, t0=a["tT"], P0=a["PT"],
+                  correct_flags=m["flags"][T1:], xy_index_map=m["ymap"][T1:], **kw)
+    np.testing.assert_array_equal(b["xT"], whole["xT"])
+    np.testing.assert_array_equal(b["PT"], whole["PT"])
+    assert abs((a["nll"] + b["nll"])[0] - whole["nll"][0]) <= 1e-12 * abs(whole["nll"][0])
+
+
+def test_per_trajectory_params_and_observations():
+    """theta [B,p] and ys [T_obs,B,L] per trajectory give the same result as B separate runs."""
+    import util as U
+    spec = cases.CASES["lv_rkf45_temper_q_only"]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    rng = np.random.default_rng(3)
+    B = 3
+    theta = plan.default_params[None, :] * (1 + 0.1 * rng.uniform(-1, 1, (B, plan.p)))
+    ys = m["ys"].numpy()[:, None, :] + 0.01 * rng.normal(size=(m["ys"].shape[0], B, m["L"]))
+    x0 = m["x0"].reshape(1, -1).numpy() + 0.05 * rng.normal(size=(B, m["n"]))
+    common = dict(t0=m["t0"], P0_sqrt=m["P0s"].numpy(), Q_sqrt=m["Q"].numpy(),
+                  gamma_sqrt=m["gamma"] ** 0.5, H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(),
+                  correct_flags=m["flags"], xy_index_map=m["ymap"])
+    batched = U.run_ekf("hostemu", plan, x0, m["T"], theta=theta, ys=ys, ys_per_trajectory=True, **common)
+    for b in range(B):
+        one = U.run_ekf("hostemu", plan, x0[b:b + 1], m["T"], theta_shared=theta[b], ys=ys[:, b], **common)
+        np.testing.assert_array_equal(batched["xT"][b], one["xT"][0])
+        np.testing.assert_array_equal(batched["PT"][b], one["PT"][0])
+        np.testing.assert_array_equal(batched["nll"][b], one["nll"][0])
+
+
+def test_nan_propagates_per_trajectory_without_error():
+    """Numerical failure is never an error: a NaN trajectory stays NaN, its
+    neighbours are untouched."""
+    import util as U
+    spec = cases.CASES["lorenz_rkf45_obs_full"]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    x0 = np.repeat(m["x0"].reshape(1, -1).numpy(), 3, axis=0)
+    x0[1, 0] = np.nan
+    out = U.run_ekf("hostemu", plan, x0, 20, P0_sqrt=m["P0s"].numpy(), H=m["H"].numpy(),
+                    R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy(), correct_flags=m["flags"],
+                    xy_index_map=m["ymap"])
+    assert np.isnan(out["xT"][1]).all() and np.isnan(out["nll"][1])
+    assert np.isfinite(out["xT"][[0, 2]]).all()
+    np.testing.assert_array_equal(out["xT"][0], out["xT"][2])
+
+
+def test_invalid_arguments_raise_value_error():
+    import util as U
+    from ode_uncertainty_b200 import Plan, _native as N
+    with pytest.raises(ValueError):
+        Plan(ode_id=N.ODE_LORENZ, solver_id=17, step_size=0.01)
+    with pytest.raises(ValueError):
+        Plan(ode_id=N.ODE_LORENZ, solver_id=N.SOLVER_RKF45, step_size=-1.0)
+    with pytest.raises(ValueError):
+        Plan(ode_id=N.ODE_MULTI_HH, solver_id=N.SOLVER_RKF45, step_size=0.01, ode_variant=1,
+             num_compartments=5)
+    plan = Plan(ode_id=N.ODE_LORENZ, solver_id=N.SOLVER_RKF45, step_size=0.01)
+    with pytest.raises(ValueError):  # L > n
+        U.run_ekf("hostemu", plan, np.ones((1, 3)), 5, H=np.ones((4, 3)), R_sqrt=np.eye(4),
+                  ys=np.zeros((5, 4)), correct_flags=np.ones(5, np.uint8),
+                  xy_index_map=np.arange(5))

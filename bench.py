@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the batched EKF-over-embedded-RK path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload = "C2"): BASELINE config 2 - batched EKF over 65,536 random initial
+conditions per GPU, Lorenz-63 and Van der Pol, RKF45 h=0.01, T=10,000 steps, predict + correct +
+log-likelihood at every step (H = I, R = 1e-3 I, one shared noisy observation sequence of the
+true trajectory).  One bench "step" = one whole-trajectory pass over both batches
+(2 x 65,536 x 10,000 trajectory-steps per GPU).  Weak scaling: every rank runs its own 65,536
+trajectories; there is no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic flops per trajectory-step, SURVEY 8(d) / BASELINE.md section 3 (full-covariance
+# count; FMA = 2): predict + correct
+F_STEP = {"Lorenz": 1155.0, "VanDerPol": 501.0}
+F_STEP_PREDICT = {"Lorenz": 777.0, "VanDerPol": 380.0}
+METRIC = "ekf_rk_trajectory_steps_per_sec"
+UNIT = "trajectory-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--B", type=int, default=65536, help="trajectories per GPU (config: 65536)")
+    ap.add_argument("--T", type=int, default=10000, help="steps per trajectory (config: 10000)")
+    ap.add_argument("--cpu-sample-B", type=int, default=0, help="CPU baseline sample size (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def workload_inputs(system: str, B: int, T: int, rank: int):
+    """Synthetic inputs of SURVEY 8(d) C2 (host numpy)."""
+    rng = np.random.default_rng(7 + 1000 * rank)
+    if system == "Lorenz":
+        n, x_true0, spread, t0 = 3, np.array([1.0, 1.0, 1.0]), 5.0, 0.0
+    else:
+        n, x_true0, spread, t0 = 2, np.array([2.0, 10.0]), 1.0, 10.0
+    x0 = x_true0 + rng.uniform(-spread, spread, (B, n))
+    P0_sqrt = np.eye(n) * (spread / 3 ** 0.5)          # std of U(-spread, spread)
+    H = np.eye(n)
+    R_sqrt = np.eye(n) * 1e-3 ** 0.5
+    return dict(n=n, x_true0=x_true0, x0=x0, P0_sqrt=P0_sqrt, H=H, R_sqrt=R_sqrt, t0=t0)
+
+
+def observations(system: str, T: int, w):
+    """Shared observation sequence: the true trajectory (noise-free RK from x_true0, CPU
+    restatement) + N(0, 1e-3), default_rng(8)."""
+    from oracle import ref_cpp as RC
+    th = {"Lorenz": [10.0, 8.0 / 3, 28.0], "VanDerPol": [5.0]}[system]
+    xs, _ = RC.rk_run(system, "RKF45", 0.01, w["x_true0"], T, t0=w["t0"], theta=th)
+    rng = np.random.default_rng(8)
+    return xs[1:] + rng.normal(0.0, 1e-3 ** 0.5, (T, w["n"]))
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4)
+                          if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(B_s: int, T_s: int, nthreads: int = 0):
+    """Times the reference's CPU algorithm (Oracle-B: C++ restatement of the square-root EKF,
+    all host threads) on a bounded sample of the same workload; returns (traj-steps/s, cores,
+    sample description, seconds)."""
+    from oracle import ref_cpp as RC
+    cores = RC.num_threads() if nthreads <= 0 else nthreads
+    units, secs = 0, 0.0
+    for system in ("Lorenz", "VanDerPol"):
+        w = workload_inputs(system, B_s, T_s, 0)
+        ys = observations(system, T_s, w)
+        th = {"Lorenz": [10.0, 8.0 / 3, 28.0], "VanDerPol": [5.0]}[system]
+        flags, ymap = np.ones(T_s, np.uint8), np.arange(T_s, dtype=np.int64)
+        t = time.perf_counter()
+        RC.ekf_run(system, "RKF45", 0.01, w["x0"], T_s, t0=w["t0"], P0_sqrt=w["P0_sqrt"], theta=th,
+                   H=w["H"], R_sqrt=w["R_sqrt"], ys=ys, correct_flags=flags, xy_index_map=ymap,
+                   nthreads=cores)
+        secs += time.perf_counter() - t
+        units += B_s * T_s
+    return units / secs, cores, f"Lorenz+VanDerPol, B={B_s} trajectories x T={T_s} steps each, Oracle-B sqrt-EKF", secs
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU formulation of the path (Oracle-B; the JAX
+    reference cannot be installed offline: jax/jaxlib/diffrax/jaxopt are absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B_s = args.cpu_sample_B or 512
+    T_s = 1000
+    rate0, cores, sample, secs = cpu_reference_rate(B_s, T_s)        # sizing probe (also warm-up)
+    target = 8.0                                                     # seconds per timed step
+    B_s = int(max(64, min(65536, B_s * target / max(secs, 1e-3))))
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_reference_rate(min(B_s, 256), 200)
+    tot_units, tot_secs = 0.0, 0.0
+    for _ in range(args.steps):
+        rate, cores, sample, secs = cpu_reference_rate(B_s, T_s)
+        tot_units += rate * secs
+        tot_secs += secs
+    value = tot_units / tot_secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C2", "systems": ["Lorenz", "VanDerPol"], "solver": "RKF45", "h": 0.01,
+                   "observations": "every step, H=I, R=1e-3 I, shared sequence",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ode_uncertainty_b200 import Plan, _native as N, ekf_run, launch_count
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = args.B, args.T
+
+    plans, inp = {}, {}
+    for system, ode_id in (("Lorenz", N.ODE_LORENZ), ("VanDerPol", N.ODE_VAN_DER_POL)):
+        plans[system] = Plan(ode_id=ode_id, solver_id=N.SOLVER_RKF45, step_size=0.01)
+        w = workload_inputs(system, B, T, rank)
+        ys = observations(system, T, w)
+        w["x0_host"] = torch.from_numpy(w["x0"]).pin_memory()
+        w["ys_host"] = torch.from_numpy(ys).pin_memory()
+        w["x0_dev"] = w["x0_host"].to(dev)
+        w["ys_dev"] = w["ys_host"].to(dev)
+        w["flags"] = torch.ones(T, dtype=torch.uint8, device=dev)
+        w["ymap"] = torch.arange(T, dtype=torch.int64, device=dev)
+        inp[system] = w
+
+    def one(system, x0_dev, ys_dev):
+        w = inp[system]
+        return ekf_run(plans[system], x0_dev, T, t0=w["t0"], P0_sqrt=w["P0_sqrt"], H=w["H"],
+                       R_sqrt=w["R_sqrt"], ys=ys_dev, correct_flags=w["flags"], xy_index_map=w["ymap"])
+
+    def step_resident():
+        return [one(s, inp[s]["x0_dev"], inp[s]["ys_dev"]) for s in ("Lorenz", "VanDerPol")]
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- FP64 pipe peak (roofline denominator), measured here with the library's DFMA kernel
+    import ctypes as C
+    scratch = torch.zeros(8, dtype=torch.float64, device=dev)
+    flops = C.c_double(0.0)
+    st = torch.cuda.current_stream(dev)
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        N.check(N.lib().odeu_bench_dfma(200000, 148 * 8, 256, C.c_void_p(scratch.data_ptr()),
+                                        C.byref(flops), C.c_void_p(st.cuda_stream)), "odeu_bench_dfma")
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3))
+    dfma_peak_tflops = best / 1e12
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        res = step_resident()
+    barrier()
+
+    # ---- timed region (device-resident inputs): K steps, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = launch_count()
+    step_ms, lorenz_ms, vdp_ms = [], [], []
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        r_l = one("Lorenz", inp["Lorenz"]["x0_dev"], inp["Lorenz"]["ys_dev"])
+        ev[1].record()
+        r_v = one("VanDerPol", inp["VanDerPol"]["x0_dev"], inp["VanDerPol"]["ys_dev"])
+        ev[2].record()
+        torch.cuda.synchronize()
+        lorenz_ms.append(ev[0].elapsed_time(ev[1]))
+        vdp_ms.append(ev[1].elapsed_time(ev[2]))
+        step_ms.append(ev[0].elapsed_time(ev[2]))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = launch_count() - launches0
+    clocks = sampler.stop()
+    t_local = sum(step_ms) * 1e-3
+    tt = torch.tensor([t_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt.item())
+    units_per_step = 2.0 * B * T * world
+    value = units_per_step * args.steps / t_max
+    finite = bool(torch.isfinite(r_l.nll).all() and torch.isfinite(r_v.nll).all())
+
+    # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region
+    out_host = {s: (torch.empty(B, inp[s]["n"], dtype=torch.float64).pin_memory(),
+                    torch.empty(B, dtype=torch.float64).pin_memory()) for s in inp}
+    h2d = sum(inp[s]["x0_host"].numel() * 8 + inp[s]["ys_host"].numel() * 8 for s in inp)
+    d2h = sum(out_host[s][0].numel() * 8 + out_host[s][1].numel() * 8 for s in inp)
+
+    def step_e2e():
+        for s in ("Lorenz", "VanDerPol"):
+            x0d = inp[s]["x0_host"].to(dev, non_blocking=True)
+            ysd = inp[s]["ys_host"].to(dev, non_blocking=True)
+            r = one(s, x0d, ysd)
+            out_host[s][0].copy_(r.xT, non_blocking=True)
+            out_host[s][1].copy_(r.nll, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    barrier()
+    e2e_t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_local = time.perf_counter() - e2e_t0
+    et = torch.tensor([e2e_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_step * args.steps / float(et.item())
+
+    # ---- extras (rank 0, N=1): predict-only and streaming variants of the dominant kernel
+    extras = {}
+    if rank == 0:
+        def timed(fn, reps=2):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+            return min(ts)
+        w = inp["Lorenz"]
+        t_pred = timed(lambda: ekf_run(plans["Lorenz"], w["x0_dev"], T, P0_sqrt=np.eye(3) * 1e-12))
+        extras["lorenz_predict_only_traj_steps_per_s"] = B * T / t_pred
+        extras["lorenz_predict_only_frac_fp64_peak"] = F_STEP_PREDICT["Lorenz"] * B * T / t_pred / 1e12 / dfma_peak_tflops
+        # streaming variant: save t,x,eps,P every step (128 B per trajectory-step at n=3) for a
+        # shorter horizon so the output (B * Ts * 21 * 8 B) stays bounded
+        Ts = min(T, 512)
+        t_str = timed(lambda: ekf_run(plans["Lorenz"], w["x0_dev"], Ts, P0_sqrt=np.eye(3) * 1e-12,
+                                      save_interval=1, save_keys=("x", "eps", "P")), reps=1)
+        bytes_str = B * (Ts + 1) * (3 + 3 + 9) * 8
+        extras["lorenz_streaming_save_every_step"] = {"traj_steps_per_s": B * Ts / t_str,
+                                                      "hbm_write_GBps": bytes_str / t_str / 1e9}
+        extras["vdp_traj_steps_per_s"] = B * T / (np.mean(vdp_ms) * 1e-3)
+        extras["lorenz_traj_steps_per_s"] = B * T / (np.mean(lorenz_ms) * 1e-3)
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        B_s = args.cpu_sample_B or 1024
+        rate, cores, sample, secs = cpu_reference_rate(B_s, 1000)
+        if secs < 5.0:   # scale the sample to ~10-20 s of CPU work
+            B_s = int(B_s * 12.0 / max(secs, 1e-3))
+            rate, cores, sample, secs = cpu_reference_rate(B_s, 1000)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "seconds": secs}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        lor_s = float(np.mean(lorenz_ms)) * 1e-3
+        achieved = F_STEP["Lorenz"] * B * T / lor_s / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C2", "systems": ["Lorenz", "VanDerPol"], "B_per_gpu": B, "T": T,
+                       "solver": "RKF45", "h": 0.01,
+                       "observations": "every step, H=I, R=1e-3 I, shared sequence",
+                       "units_per_step": units_per_step, "l2": "flushed (256 MB write) between timed steps",
+                       "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
+            "roofline": {"bound": "fp64", "kernel": "ekf_thread_kernel<OdeLorenz,TabRKF45>",
+                         "achieved": achieved, "peak": dfma_peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / dfma_peak_tflops,
+                         "peak_source": "measured in this run: odeu_bench_dfma (8 DFMA chains/thread, 148x8x256 threads)",
+                         "algorithmic_flops_per_unit": F_STEP["Lorenz"], "units_per_launch": B * T,
+                         "avg_launch_ms": lor_s * 1e3, "traffic": None,
+                         "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "wall_s_timed_region": wall,
+            "all_finite": finite,
+            "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

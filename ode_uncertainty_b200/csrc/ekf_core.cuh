@@ -234,6 +234,24 @@ ODEU_HD void add_process_noise(int noise_mode, int cov_fn, double scale,
   }
 }
 
+// Where a measurement update publishes the PRE-update y_hat and S that the reference keeps in
+// its state dict (sqrt_ekf.py:370-372).  They are written straight to the caller's output
+// buffers (trajectory slot and/or final-state arrays; batch-minor, stride B) instead of being
+// carried in registers for the whole run.
+struct ObsSink {
+  double* y1; double* S1;   // upcoming trajectory slot (nullable)
+  double* y2; double* S2;   // final-state outputs (nullable)
+  long long stride;
+  ODEU_HD void put_y(int l, double v) const {
+    if (y1) y1[l * stride] = v;
+    if (y2) y2[l * stride] = v;
+  }
+  ODEU_HD void put_S(int idx, double v) const {
+    if (S1) S1[idx * stride] = v;
+    if (S2) S2[idx * stride] = v;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Measurement update + log-likelihood term.  L (<= n) is a run-time value; all loops are
 // statically bounded by n and guarded so small systems stay in registers.
@@ -242,10 +260,11 @@ ODEU_HD void add_process_noise(int noise_mode, int cov_fn, double scale,
 template <int n>
 ODEU_HD double correct_step(int L, const double* H, const double* R,
                                                const double* y, double* x, double (*P)[n],
-                                               double* yhat, double (*Smat)[n]) {
+                                               const ObsSink& sink) {
   constexpr int U = (n <= 4) ? n : 1;
   double PHt[n][n];  // [n][L]
   double d[n];
+  double Smat[n][n];
   // y_hat = H x, PHt = P H^T
 #pragma unroll U
   for (int l = 0; l < n; ++l) {
@@ -253,7 +272,7 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
       double s = 0.0;
 #pragma unroll U
       for (int j = 0; j < n; ++j) s = fma(H[l * n + j], x[j], s);
-      yhat[l] = s;
+      sink.put_y(l, s);
       d[l] = y[l] - s;
 #pragma unroll U
       for (int i = 0; i < n; ++i) {
@@ -275,10 +294,13 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
         for (int j = 0; j < n; ++j) s = fma(H[l * n + j], PHt[j][m], s);
         Smat[l][m] = s;
         Smat[m][l] = s;
+        sink.put_S(l * L + m, s);
+        if (m != l) sink.put_S(m * L + l, s);
       }
     }
-  // Cholesky S = Ls Ls^T
-  double Ls[n][n];
+  // Cholesky S = Ls Ls^T; the reciprocal diagonal is kept so every later triangular solve
+  // multiplies instead of dividing (FP64 division costs ~10x a DFMA on the FP64 pipe)
+  double Ls[n][n], inv[n];
   bool all_tiny = true;
 #pragma unroll U
   for (int j = 0; j < n; ++j) {
@@ -289,14 +311,14 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
       const double dj = sqrt(s);
       Ls[j][j] = dj;
       all_tiny = all_tiny && (fabs(dj) < 1e-16);
-      const double inv = 1.0 / dj;
+      inv[j] = 1.0 / dj;
 #pragma unroll U
       for (int i = j + 1; i < n; ++i) {
         if (i < L) {
           double v = Smat[i][j];
 #pragma unroll U
           for (int k = 0; k < j; ++k) v = fma(-Ls[i][k], Ls[j][k], v);
-          v *= inv;
+          v *= inv[j];
           Ls[i][j] = v;
           all_tiny = all_tiny && (fabs(v) < 1e-16);
         }
@@ -312,7 +334,7 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
       double s = d[i];
 #pragma unroll U
       for (int k = 0; k < i; ++k) s = fma(-Ls[i][k], z[k], s);
-      z[i] = s / Ls[i][i];
+      z[i] = s * inv[i];
       quad = fma(z[i], z[i], quad);
       logdet += log(fabs(Ls[i][i]));
     }
@@ -336,7 +358,7 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
           double s = PHt[i][l];
 #pragma unroll U
           for (int k = 0; k < l; ++k) s = fma(-Ls[l][k], w[k], s);
-          w[l] = s / Ls[l][l];
+          w[l] = s * inv[l];
         }
       }
 #pragma unroll U
@@ -346,7 +368,7 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
 #pragma unroll U
           for (int k = l + 1; k < n; ++k)
             if (k < L) s = fma(-Ls[k][l], K[i][k], s);
-          K[i][l] = s / Ls[l][l];
+          K[i][l] = s * inv[l];
         }
       }
     }
@@ -396,6 +418,139 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
 #pragma unroll U
       for (int l = 0; l < n; ++l)
         if (l < L) s = fma(-G[i][l], K[j][l], s);
+      P[i][j] = s;
+      P[j][i] = s;
+    }
+  return nlg;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Measurement update specialised at compile time for H = [I_L 0] (the first L state components
+// are observed directly) - the shape of every measurement_matrix the reference ships for small
+// systems ('[[1, 0]]', identity, ...; configs/*/*.yaml).  Same mathematics as correct_step:
+// H P = first L rows of P, so the H products disappear; Cholesky pivots use rsqrt, all solves
+// multiply by the stored reciprocals, and sum(log Ls_ii) = 0.5 log(prod pivots) needs one log.
+template <int n, int L>
+ODEU_HD double correct_step_lead(const double* R, const double* y, double* x, double (*P)[n],
+                                 const ObsSink& sink) {
+  double d[L], Ls[L][L], inv[L], Smat[L][L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    sink.put_y(l, x[l]);
+    d[l] = y[l] - x[l];
+#pragma unroll
+    for (int m = 0; m <= l; ++m) {
+      const double s = P[l][m] + R[l * L + m];
+      Smat[l][m] = s;
+      sink.put_S(l * L + m, s);
+      if (m != l) sink.put_S(m * L + l, s);
+    }
+  }
+  bool all_tiny = true;
+  double piv = 1.0;
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    double s = Smat[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s = fma(-Ls[j][k], Ls[j][k], s);
+    piv *= s;
+    const double r = rsqrt(s);
+    const double dj = s * r;             // sqrt(s) up to an ulp; NaN for s < 0 like sqrt
+    inv[j] = r;
+    Ls[j][j] = dj;
+    all_tiny = all_tiny && (fabs(dj) < 1e-16);
+#pragma unroll
+    for (int i = j + 1; i < L; ++i) {
+      double v = Smat[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-Ls[i][k], Ls[j][k], v);
+      v *= r;
+      Ls[i][j] = v;
+      all_tiny = all_tiny && (fabs(v) < 1e-16);
+    }
+  }
+  double z[L], quad = 0.0;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    double s = d[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s = fma(-Ls[i][k], z[k], s);
+    z[i] = s * inv[i];
+    quad = fma(z[i], z[i], quad);
+  }
+  // sum_i log|Ls_ii| = 0.5 log(prod_i pivot_i); fall back to the sum when the product leaves
+  // the normal range (or a pivot is non-positive / NaN)
+  double logdet;
+  if (piv > 1e-290 && piv < 1e290) {
+    logdet = 0.5 * log(piv);
+  } else {
+    logdet = 0.0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) logdet += log(fabs(Ls[i][i]));
+  }
+  const double nlg = 0.5 * quad + 0.5 * (double)L * 1.8378770664093453 + logdet;
+
+  double K[n][L];
+  if (all_tiny) {
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+      for (int l = 0; l < L; ++l) K[i][l] = 0.0;
+  } else {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      double w[L];
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        double s = P[i][l];
+#pragma unroll
+        for (int k = 0; k < l; ++k) s = fma(-Ls[l][k], w[k], s);
+        w[l] = s * inv[l];
+      }
+#pragma unroll
+      for (int l = L - 1; l >= 0; --l) {
+        double s = w[l];
+#pragma unroll
+        for (int k = l + 1; k < L; ++k) s = fma(-Ls[k][l], K[i][k], s);
+        K[i][l] = s * inv[l];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    double s = x[i];
+#pragma unroll
+    for (int l = 0; l < L; ++l) s = fma(K[i][l], d[l], s);
+    x[i] = s;
+  }
+  // Joseph with H = [I_L 0]:  AP = P - K P[:L,:];  G = AP[:, :L] - K R;  P+ = AP - G K^T
+  double AP[n][n];
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      double s = P[i][j];
+#pragma unroll
+      for (int l = 0; l < L; ++l) s = fma(-K[i][l], P[l][j], s);
+      AP[i][j] = s;
+    }
+  double G[n][L];
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      double s = AP[i][l];
+#pragma unroll
+      for (int m = 0; m < L; ++m) s = fma(-K[i][m], R[m * L + l], s);
+      G[i][l] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double s = AP[i][j];
+#pragma unroll
+      for (int l = 0; l < L; ++l) s = fma(-G[i][l], K[j][l], s);
       P[i][j] = s;
       P[j][i] = s;
     }

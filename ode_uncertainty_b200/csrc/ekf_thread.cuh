@@ -47,9 +47,9 @@ struct EkfArgs {
 template <int n>
 ODEU_HD void save_slot(long long slot, long long B, long long b, int L,
                                           const double* x, const double* eps,
-                                          const double (*P)[n], const double* yhat,
-                                          const double (*Smat)[n], double* out_x, double* out_eps,
-                                          double* out_P, double* out_yhat, double* out_S) {
+                                          const double (*P)[n], bool obs_fresh, double* out_x,
+                                          double* out_eps, double* out_P, double* out_yhat,
+                                          double* out_S) {
   constexpr int U = (n <= 4) ? n : 1;
 #pragma unroll U
   for (int i = 0; i < n; ++i) {
@@ -62,23 +62,23 @@ ODEU_HD void save_slot(long long slot, long long B, long long b, int L,
 #pragma unroll U
       for (int j = 0; j < n; ++j) out_P[(slot * n * n + i * n + j) * B + b] = P[i][j];
   }
-#pragma unroll U
-  for (int l = 0; l < n; ++l) {
-    if (l < L) {
-      if (out_yhat) out_yhat[(slot * L + l) * B + b] = yhat[l];
-      if (out_S) {
-#pragma unroll U
-        for (int m = 0; m < n; ++m)
-          if (m < L) out_S[(slot * L * L + l * L + m) * B + b] = Smat[l][m];
-      }
-    }
+  // y_hat / S of the most recent measurement update were already written into this slot by
+  // ObsSink; when no update happened since the previous slot the reference state still holds
+  // the older values (zeros before the first update): carry them forward.
+  if (!obs_fresh) {
+    for (int l = 0; l < L; ++l)
+      if (out_yhat) out_yhat[(slot * L + l) * B + b] = slot > 0 ? out_yhat[((slot - 1) * L + l) * B + b] : 0.0;
+    for (int l = 0; l < L * L; ++l)
+      if (out_S) out_S[(slot * L * L + l) * B + b] = slot > 0 ? out_S[((slot - 1) * L * L + l) * B + b] : 0.0;
   }
 }
 
 // The whole life of trajectory `b`.  __host__ __device__ so the identical source can be
 // exercised on the CPU by the test-only host emulation (tests/host_emu.cu); the product only
 // ever calls it from the kernel below.
-template <class Ode, class Tab, int KC>
+// LK selects the measurement-update code at compile time: -1 = generic (run-time L, dense H),
+// 0 = prediction only, 1..n = H = [I_LK 0] (correct_step_lead).
+template <class Ode, class Tab, int KC, int LK>
 ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long b) {
   constexpr int n = Ode::NX;
   constexpr int NP = Ode::NP;
@@ -86,16 +86,19 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   const long long B = a.B;
   const int L = a.L;
 
-  double x[n], eps[n], P[n][n], yhat[n], Smat[n][n], th[NP];
+  double x[n], eps[n], P[n][n], th[NP];
 #pragma unroll U
-  for (int i = 0; i < n; ++i) { x[i] = a.x0[i * B + b]; eps[i] = 0.0; yhat[i] = 0.0; }
+  for (int i = 0; i < n; ++i) { x[i] = a.x0[i * B + b]; eps[i] = 0.0; }
 #pragma unroll U
   for (int i = 0; i < n; ++i)
 #pragma unroll U
-    for (int j = 0; j < n; ++j) {
-      P[i][j] = a.P0 ? a.P0[(i * n + j) * B + b] : a.P0s[i * n + j];
-      Smat[i][j] = 0.0;
-    }
+    for (int j = 0; j < n; ++j) P[i][j] = a.P0 ? a.P0[(i * n + j) * B + b] : a.P0s[i * n + j];
+  // final-state y_hat / S start at zero like SQRT_EKF.init_state (sqrt_ekf.py:80-82)
+  for (int l = 0; l < L; ++l)
+    if (a.yhatT) a.yhatT[l * B + b] = 0.0;
+  for (int l = 0; l < L * L; ++l)
+    if (a.ST) a.ST[l * B + b] = 0.0;
+  bool obs_fresh = false;
 #pragma unroll
   for (int k = 0; k < NP; ++k) th[k] = a.theta ? a.theta[k * B + b] : a.theta_shared[k];
 
@@ -104,7 +107,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   const double h = a.h;
   const long long si = a.save_interval;
   if (si > 0) {
-    save_slot<n>(0, B, b, L, x, eps, P, yhat, Smat, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+    save_slot<n>(0, B, b, L, x, eps, P, false, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
     if (b == 0 && a.out_t) a.out_t[0] = t;
   }
   long long next_save = si;  // step count at which the next slot is written
@@ -134,18 +137,39 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     t = t + h;  // accumulated like rksolver.py:145 (stage times depend on it)
 
     // ---- correct + log-likelihood (src/filters/sqrt_ekf.py:337-376, src/utils.py:109-128)
-    if (a.has_obs && a.flags[step]) {
-      const long long oi = a.ymap[step];
-      double y[n];
+    ObsSink sink;
+    sink.stride = B;
+    const bool slot_ahead = si > 0 && next_save <= a.T;   // a further save point exists
+    sink.y1 = (slot_ahead && a.out_yhat) ? a.out_yhat + slot * L * B + b : nullptr;
+    sink.S1 = (slot_ahead && a.out_S) ? a.out_S + slot * L * L * B + b : nullptr;
+    sink.y2 = a.yhatT ? a.yhatT + b : nullptr;
+    sink.S2 = a.ST ? a.ST + b : nullptr;
+    if constexpr (LK == -1) {
+      if (a.has_obs && a.flags[step]) {
+        const long long oi = a.ymap[step];
+        double y[n];
 #pragma unroll U
-      for (int l = 0; l < n; ++l)
-        if (l < L) y[l] = a.ys_per_traj ? a.ys[(oi * L + l) * B + b] : a.ys[oi * L + l];
-      nll += correct_step<n>(L, a.H, a.R, y, x, P, yhat, Smat);
+        for (int l = 0; l < n; ++l)
+          if (l < L) y[l] = a.ys_per_traj ? a.ys[(oi * L + l) * B + b] : a.ys[oi * L + l];
+        nll += correct_step<n>(L, a.H, a.R, y, x, P, sink);
+        obs_fresh = true;
+      }
+    } else if constexpr (LK > 0) {
+      if (a.flags[step]) {
+        const long long oi = a.ymap[step];
+        double y[LK];
+#pragma unroll
+        for (int l = 0; l < LK; ++l)
+          y[l] = a.ys_per_traj ? a.ys[(oi * LK + l) * B + b] : a.ys[oi * LK + l];
+        nll += correct_step_lead<n, LK>(a.R, y, x, P, sink);
+        obs_fresh = true;
+      }
     }
 
     // ---- strided save (scripts/run_filter.py:219-222)
     if (si > 0 && step + 1 == next_save) {
-      save_slot<n>(slot, B, b, L, x, eps, P, yhat, Smat, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+      save_slot<n>(slot, B, b, L, x, eps, P, obs_fresh, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+      obs_fresh = false;
       if (b == 0 && a.out_t) a.out_t[slot] = t;
       ++slot;
       next_save += si;
@@ -164,27 +188,16 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 #pragma unroll U
       for (int j = 0; j < n; ++j) a.PT[(i * n + j) * B + b] = P[i][j];
   }
-#pragma unroll U
-  for (int l = 0; l < n; ++l) {
-    if (l < L) {
-      if (a.yhatT) a.yhatT[l * B + b] = yhat[l];
-      if (a.ST) {
-#pragma unroll U
-        for (int m = 0; m < n; ++m)
-          if (m < L) a.ST[(l * L + m) * B + b] = Smat[l][m];
-      }
-    }
-  }
   if (a.nll) a.nll[b] = nll;
   if (b == 0 && a.tT) a.tT[0] = t;
 }
 
-template <class Ode, class Tab, int KC, int BLOCK, int MINB>
+template <class Ode, class Tab, int KC, int LK, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 ekf_thread_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a) {
   const long long b = (long long)blockIdx.x * BLOCK + threadIdx.x;
   if (b >= a.B) return;
-  ekf_trajectory<Ode, Tab, KC>(a, b);
+  ekf_trajectory<Ode, Tab, KC, LK>(a, b);
 }
 
 }  // namespace odeu

@@ -79,14 +79,43 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
   return 0;
 }
 
+// Which compile-time measurement-update variant serves this run (see ekf_trajectory's LK):
+// small systems get 0 (prediction only), 1 and n when H is the leading identity block
+// (every measurement_matrix the reference ships for them), everything else the generic code.
+template <class Ode>
+int select_lk(const odeu_ekf_io& io) {
+  constexpr int n = Ode::NX;
+  if (n > 4) return -1;
+  if (io.L == 0) return 0;
+  if (io.L != 1 && io.L != n) return -1;
+  for (int l = 0; l < io.L; ++l)
+    for (int j = 0; j < n; ++j)
+      if (io.H[l * n + j] != ((l == j) ? 1.0 : 0.0)) return -1;
+  return io.L;
+}
+
+template <class Ode, class Tab, int LK>
+void launch_ekf_variant(const EkfArgs<Ode::NX, Ode::NP>& a, cudaStream_t stream) {
+  using Cfg = LaunchCfg<Ode>;
+  const long long grid = (a.B + Cfg::BLOCK - 1) / Cfg::BLOCK;
+  ekf_thread_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB>
+      <<<(unsigned)grid, Cfg::BLOCK, 0, stream>>>(a);
+}
+
 template <class Ode, class Tab>
 int launch_ekf(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream) {
-  using Cfg = LaunchCfg<Ode>;
+  constexpr int n = Ode::NX;
   EkfArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_ekf_args<Ode>(plan, io, a)) return rc;
-  const long long grid = (io.B + Cfg::BLOCK - 1) / Cfg::BLOCK;
-  ekf_thread_kernel<Ode, Tab, Cfg::KC, Cfg::BLOCK, Cfg::MINB>
-      <<<(unsigned)grid, Cfg::BLOCK, 0, stream>>>(a);
+  const int lk = select_lk<Ode>(io);
+  if constexpr (n <= 4) {
+    if (lk == 0) launch_ekf_variant<Ode, Tab, 0>(a, stream);
+    else if (lk == 1) launch_ekf_variant<Ode, Tab, 1>(a, stream);
+    else if (lk == n) launch_ekf_variant<Ode, Tab, n>(a, stream);
+    else launch_ekf_variant<Ode, Tab, -1>(a, stream);
+  } else {
+    launch_ekf_variant<Ode, Tab, -1>(a, stream);
+  }
   count_launch();
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {

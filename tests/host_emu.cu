@@ -19,7 +19,19 @@ template <class Ode, class Tab>
 int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
   EkfArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_ekf_args<Ode>(plan, io, a)) return rc;
-  for (long long b = 0; b < io.B; ++b) ekf_trajectory<Ode, Tab, LaunchCfg<Ode>::KC>(a, b);
+  constexpr int n = Ode::NX;
+  constexpr int KC = LaunchCfg<Ode>::KC;
+  const int lk = select_lk<Ode>(io);
+  for (long long b = 0; b < io.B; ++b) {
+    if constexpr (n <= 4) {
+      if (lk == 0) ekf_trajectory<Ode, Tab, KC, 0>(a, b);
+      else if (lk == 1) ekf_trajectory<Ode, Tab, KC, 1>(a, b);
+      else if (lk == n) ekf_trajectory<Ode, Tab, KC, n>(a, b);
+      else ekf_trajectory<Ode, Tab, KC, -1>(a, b);
+    } else {
+      ekf_trajectory<Ode, Tab, KC, -1>(a, b);
+    }
+  }
   return 0;
 }
 template <class Ode, class Tab>

@@ -36,7 +36,7 @@ UNIT = "trajectory-steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--B", type=int, default=65536, help="trajectories per GPU (config: 65536)")
@@ -71,38 +71,48 @@ def observations(system: str, T: int, w):
     return xs[1:] + rng.normal(0.0, 1e-3 ** 0.5, (T, w["n"]))
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region (one long-lived
+    `nvidia-smi -lms 50` process; B200_PROFILING.md clocks line)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)   # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[c.strip() for c in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+        num = lambda v: v.replace(".", "", 1).isdigit()
+        sm = [float(r[0]) for r in rows if r and num(r[0])]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and num(r[1])]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and num(r[2])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4)
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4)
                           if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        # "under load" = samples drawing clearly more than idle power
+        load = [s_ for s_, p_ in zip(sm, pw) if p_ > 250.0] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "reasons": reasons, "samples": len(rows), "samples_under_load": len(load)}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -37,10 +37,19 @@ enum CovFn { COV_DIAGONAL = 0, COV_OUTER = 1, COV_STATIC_DIAGONAL = 2 };
 //   x_next[r] = x + h * (ks @ b[r]),  propagate r=1,  eps = |x_next[0] - x_next[1]|
 // The sums skip the structural zeros of A and b; x_next[0] - x_next[1] is evaluated as the
 // difference of the two full solutions, like the reference, so eps keeps its cancellation.
+//
+// Tangent lanes carry no cancellation, so they accumulate straight into the identity seed with
+// the pre-scaled coefficients ha[i][j] = h a_ij, hb1[j] = h b_1j (kernel arguments, i.e.
+// constant-bank operands of the DFMAs): one DFMA per non-zero coefficient, no separate h-scale.
+struct ScaledTableau {
+  double ha[8][8];
+  double hb1[8];
+};
+
 template <class Ode, class Tab, int KC, class PT>
-ODEU_HD void rk_step_tangent(double t, double h, const double* x, const PT* th,
-                                                int c0, bool want_primal, double* xn, double* eps,
-                                                double (*Jcols)[KC]) {
+ODEU_HD void rk_step_tangent(double t, double h, const ScaledTableau& st, const double* x,
+                             const PT* th, int c0, bool want_primal, double* xn, double* eps,
+                             double (*Jcols)[KC]) {
   constexpr int n = Ode::NX;
   constexpr int S = Tab::S;
   using D = Dual<KC>;
@@ -61,56 +70,44 @@ ODEU_HD void rk_step_tangent(double t, double h, const double* x, const PT* th,
     } else {
 #pragma unroll
       for (int m = 0; m < n; ++m) {
-        D s;
+        double sv = 0.0;
         bool first = true;
+        Xi[m] = X[m];
 #pragma unroll
         for (int j = 0; j < i; ++j) {
           if (Tab::a(i, j) != 0.0) {
-            if (first) {
-              s = Ks[j][m] * Tab::a(i, j);
-              first = false;
-            } else {
-              s.v = fma(Tab::a(i, j), Ks[j][m].v, s.v);
+            sv = first ? Ks[j][m].v * Tab::a(i, j) : fma(Tab::a(i, j), Ks[j][m].v, sv);
+            first = false;
 #pragma unroll
-              for (int k = 0; k < KC; ++k) s.d[k] = fma(Tab::a(i, j), Ks[j][m].d[k], s.d[k]);
-            }
+            for (int k = 0; k < KC; ++k) Xi[m].d[k] = fma(st.ha[i][j], Ks[j][m].d[k], Xi[m].d[k]);
           }
         }
-        if (first) {
-          Xi[m] = X[m];
-        } else {
-          Xi[m].v = fma(h, s.v, X[m].v);
-#pragma unroll
-          for (int k = 0; k < KC; ++k) Xi[m].d[k] = fma(h, s.d[k], X[m].d[k]);
-        }
+        if (!first) Xi[m].v = fma(h, sv, X[m].v);
       }
     }
     Ode::rhs(t + h * Tab::c(i), Xi, th, Ks[i]);
   }
 #pragma unroll
   for (int m = 0; m < n; ++m) {
-    D s1;
-    double s0 = 0.0;
+    double s1v = 0.0, s0 = 0.0;
     bool f1 = true, f0 = true;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) Jcols[m][k] = X[m].d[k];
 #pragma unroll
     for (int j = 0; j < S; ++j) {
       if (Tab::b(1, j) != 0.0) {
-        if (f1) { s1 = Ks[j][m] * Tab::b(1, j); f1 = false; }
-        else {
-          s1.v = fma(Tab::b(1, j), Ks[j][m].v, s1.v);
+        s1v = f1 ? Ks[j][m].v * Tab::b(1, j) : fma(Tab::b(1, j), Ks[j][m].v, s1v);
+        f1 = false;
 #pragma unroll
-          for (int k = 0; k < KC; ++k) s1.d[k] = fma(Tab::b(1, j), Ks[j][m].d[k], s1.d[k]);
-        }
+        for (int k = 0; k < KC; ++k) Jcols[m][k] = fma(st.hb1[j], Ks[j][m].d[k], Jcols[m][k]);
       }
       if (Tab::b(0, j) != 0.0) {
         if (f0) { s0 = Ks[j][m].v * Tab::b(0, j); f0 = false; }
         else s0 = fma(Tab::b(0, j), Ks[j][m].v, s0);
       }
     }
-#pragma unroll
-    for (int k = 0; k < KC; ++k) Jcols[m][k] = fma(h, s1.d[k], X[m].d[k]);
     if (want_primal) {
-      const double x1 = fma(h, s1.v, x[m]);
+      const double x1 = fma(h, s1v, x[m]);
       const double x0 = fma(h, s0, x[m]);
       xn[m] = x1;
       eps[m] = fabs(x0 - x1);

@@ -42,6 +42,7 @@ struct EkfArgs {
   double H[NX * NX];      // [L][n]
   double R[NX * NX];      // [L][L] = R_sqrt R_sqrt^T
   double theta_shared[NP];
+  ScaledTableau st;       // h * a_ij, h * b_1j
 };
 
 template <int n>
@@ -117,12 +118,12 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     // ---- predict (src/filters/sqrt_ekf.py:92-197)
     double xn[n], J[n][n];
     if constexpr (KC == n) {
-      rk_step_tangent<Ode, Tab, KC>(t, h, x, th, 0, true, xn, eps, J);
+      rk_step_tangent<Ode, Tab, KC>(t, h, a.st, x, th, 0, true, xn, eps, J);
     } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < n; c0 += KC) {
         double Jc[n][KC];
-        rk_step_tangent<Ode, Tab, KC>(t, h, x, th, c0, c0 == 0, xn, eps, Jc);
+        rk_step_tangent<Ode, Tab, KC>(t, h, a.st, x, th, c0, c0 == 0, xn, eps, Jc);
 #pragma unroll 1
         for (int i = 0; i < n; ++i)
 #pragma unroll

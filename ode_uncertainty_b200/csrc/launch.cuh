@@ -17,6 +17,14 @@ struct LaunchCfg {
 };
 
 // Validates `io` and folds the shared host matrices into the by-value kernel arguments.
+template <class Tab>
+void fill_scaled_tableau(double h, ScaledTableau& st) {
+  for (int i = 0; i < 8; ++i) {
+    st.hb1[i] = (i < Tab::S) ? h * Tab::b(1, i) : 0.0;
+    for (int j = 0; j < 8; ++j) st.ha[i][j] = (i < Tab::S && j < Tab::S) ? h * Tab::a(i, j) : 0.0;
+  }
+}
+
 template <class Ode>
 int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX, Ode::NP>& a) {
   constexpr int n = Ode::NX;
@@ -107,6 +115,7 @@ int launch_ekf(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream
   constexpr int n = Ode::NX;
   EkfArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_ekf_args<Ode>(plan, io, a)) return rc;
+  fill_scaled_tableau<Tab>(plan.desc.step_size, a.st);
   const int lk = select_lk<Ode>(io);
   if constexpr (n <= 4) {
     if (lk == 0) launch_ekf_variant<Ode, Tab, 0>(a, stream);

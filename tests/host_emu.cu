@@ -19,6 +19,7 @@ template <class Ode, class Tab>
 int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
   EkfArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_ekf_args<Ode>(plan, io, a)) return rc;
+  fill_scaled_tableau<Tab>(plan.desc.step_size, a.st);
   constexpr int n = Ode::NX;
   constexpr int KC = LaunchCfg<Ode>::KC;
   const int lk = select_lk<Ode>(io);

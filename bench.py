@@ -146,7 +146,7 @@ def run_reference_arm(args):
     B_s = args.cpu_sample_B or 512
     T_s = 1000
     rate0, cores, sample, secs = cpu_reference_rate(B_s, T_s)        # sizing probe (also warm-up)
-    target = 8.0                                                     # seconds per timed step
+    target = 4.0                                                     # seconds per timed step
     B_s = int(max(64, min(65536, B_s * target / max(secs, 1e-3))))
     for _ in range(max(args.warmup - 1, 0)):
         cpu_reference_rate(min(B_s, 256), 200)

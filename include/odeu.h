@@ -108,6 +108,8 @@ typedef struct {
   const uint8_t* correct_flags;   /* DEVICE [T]  run_filter.py:102-103 */
   const int64_t* xy_index_map;    /* DEVICE [T]  run_filter.py:104-105 */
   int64_t save_interval;     /* 0 = no trajectory output; else slots 0, s, 2s, ... (run_filter.py:219-222) */
+  int32_t skip_predict;      /* 1: apply only the measurement update in each step (single-step
+                                FilterCorrect of src/filters/filter.py:31-33; API-compat/tests) */
   /* ---- outputs (DEVICE, any may be NULL) */
   double* xT;                /* [n][B]    final mean */
   double* epsT;              /* [n][B]    last local error estimate */
@@ -145,6 +147,7 @@ typedef struct {
   int64_t particle_offset;   /* global index of local particle 0 (sharding) */
   int64_t step_offset;       /* global index of local step 0 (resume) */
   int64_t save_interval;     /* 0 = none */
+  int32_t noise_free;        /* 1: no perturbation at all = plain RK solver (src/solvers/rksolver.py:113-155) */
   double* xT;                /* DEVICE [n][M] */
   double* epsT;              /* DEVICE [n][M] */
   double* tT;                /* DEVICE [1] */
@@ -155,6 +158,12 @@ typedef struct {
 
 /* Replaces unroll() driven by ParticleFilter.build_predict (particle_filter.py:73-118). */
 int odeu_pf_run(const odeu_plan* plan, const odeu_pf_io* io, void* cuda_stream);
+
+/* ODE right-hand side dx/dt = f(t, x, theta) for a batch (the `ODE` callable of
+ * src/ode/ode.py:6-7).  x, dx: DEVICE [n][B]; theta: DEVICE [p][B] or NULL -> theta_shared (HOST
+ * [p]) or NULL -> reference defaults. */
+int odeu_ode_rhs(const odeu_plan* plan, int64_t B, double t, const double* x, const double* theta,
+                 const double* theta_shared, double* dx, void* cuda_stream);
 
 /* FP64-pipe micro-benchmark (roofline denominator for the EKF kernels): launches `blocks` x
  * `threads` threads each running 8 independent chains of `iters` dependent DFMAs; writes the

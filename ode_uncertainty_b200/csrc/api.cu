@@ -84,7 +84,7 @@ int odeu_plan_create(const odeu_plan_desc* desc, odeu_plan** out) {
     return -2;
   }
   p->p = (int)p->theta_default.size();
-  Launchers fn = {nullptr, nullptr};
+  Launchers fn = {nullptr, nullptr, nullptr};
   switch (desc->ode_id) {
     case ODEU_ODE_LORENZ: fn = resolve_lorenz(desc->solver_id); break;
     case ODEU_ODE_VAN_DER_POL: fn = resolve_van_der_pol(desc->solver_id); break;
@@ -103,6 +103,7 @@ int odeu_plan_create(const odeu_plan_desc* desc, odeu_plan** out) {
   }
   p->ekf_launch = fn.ekf;
   p->pf_launch = fn.pf;
+  p->rhs_launch = fn.rhs;
   *out = p;
   return 0;
 }
@@ -125,6 +126,12 @@ int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream
 int odeu_pf_run(const odeu_plan* plan, const odeu_pf_io* io, void* cuda_stream) {
   if (!plan || !io) { set_error("odeu_pf_run: null argument"); return -1; }
   return plan->pf_launch(*plan, *io, (cudaStream_t)cuda_stream);
+}
+
+int odeu_ode_rhs(const odeu_plan* plan, int64_t B, double t, const double* x, const double* theta,
+                 const double* theta_shared, double* dx, void* cuda_stream) {
+  if (!plan) { set_error("odeu_ode_rhs: null plan"); return -1; }
+  return plan->rhs_launch(*plan, (long long)B, t, x, theta, theta_shared, dx, (cudaStream_t)cuda_stream);
 }
 
 int64_t odeu_launch_count(void) { return (int64_t)g_launches.load(); }

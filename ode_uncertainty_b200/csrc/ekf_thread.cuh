@@ -27,6 +27,7 @@ struct EkfArgs {
   long long save_interval;  // 0: no trajectory output
   int ys_per_traj;
   int has_obs;
+  int skip_predict;       // generic variant only: measurement update without the RK/covariance step
   // device pointers
   const double* x0;
   const double* P0;       // nullable
@@ -117,6 +118,9 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   for (long long step = 0; step < a.T; ++step) {
     // ---- predict (src/filters/sqrt_ekf.py:92-197)
     double xn[n], J[n][n];
+    if (LK == -1 && a.skip_predict) {
+      // single-step FilterCorrect: leave t, x, eps, P untouched
+    } else {
     if constexpr (KC == n) {
       rk_step_tangent<Ode, Tab, KC>(t, h, a.st, x, th, 0, true, xn, eps, J);
     } else {
@@ -136,6 +140,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 #pragma unroll U
     for (int i = 0; i < n; ++i) x[i] = xn[i];
     t = t + h;  // accumulated like rksolver.py:145 (stage times depend on it)
+    }
 
     // ---- correct + log-likelihood (src/filters/sqrt_ekf.py:337-376, src/utils.py:109-128)
     ObsSink sink;

@@ -7,7 +7,7 @@ Launchers resolve_hh(int model, int solver) {
     case 0: return resolve_solver<OdeHodgkinHuxley<0>>(solver);
     case 1: return resolve_solver<OdeHodgkinHuxley<1>>(solver);
     case 4: return resolve_solver<OdeHodgkinHuxley<4>>(solver);
-    default: return {nullptr, nullptr};
+    default: return {nullptr, nullptr, nullptr};
   }
 }
 }

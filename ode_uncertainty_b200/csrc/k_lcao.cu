@@ -4,6 +4,6 @@
 namespace odeu {
 Launchers resolve_lcao(int D, int solver) {
   if (D == 2) return resolve_solver<OdeLCAO<2>>(solver);
-  return {nullptr, nullptr};
+  return {nullptr, nullptr, nullptr};
 }
 }

@@ -43,6 +43,7 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
   a.cov_fn = plan.desc.cov_fn_id; a.cov_scale = plan.desc.cov_scale;
   a.save_interval = io.save_interval;
   a.ys_per_traj = io.ys_per_trajectory; a.has_obs = io.L > 0 ? 1 : 0;
+  a.skip_predict = io.skip_predict;
   a.x0 = io.x0; a.P0 = io.P0; a.theta = io.theta; a.ys = io.ys;
   a.flags = io.correct_flags; a.ymap = (const long long*)io.xy_index_map;
   a.xT = io.xT; a.epsT = io.epsT; a.PT = io.PT; a.yhatT = io.yhatT; a.ST = io.ST; a.nll = io.nll;
@@ -93,7 +94,7 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
 template <class Ode>
 int select_lk(const odeu_ekf_io& io) {
   constexpr int n = Ode::NX;
-  if (n > 4) return -1;
+  if (n > 4 || io.skip_predict) return -1;
   if (io.L == 0) return 0;
   if (io.L != 1 && io.L != n) return -1;
   for (int l = 0; l < io.L; ++l)
@@ -145,6 +146,7 @@ int fill_pf_args(const odeu_plan& plan, const odeu_pf_io& io, PfArgs<Ode::NX, Od
   a.cov_fn = plan.desc.cov_fn_id; a.cov_scale = plan.desc.cov_scale;
   a.seed = io.seed; a.particle_offset = io.particle_offset; a.step_offset = io.step_offset;
   a.save_interval = io.save_interval;
+  a.noise_free = io.noise_free;
   a.x0 = io.x0; a.xT = io.xT; a.epsT = io.epsT; a.tT = io.tT;
   a.out_t = io.out_t; a.out_x = io.out_x; a.out_eps = io.out_eps;
   for (int i = 0; i < n; ++i) a.x0s[i] = io.x0_shared ? io.x0_shared[i] : 0.0;
@@ -170,13 +172,27 @@ int launch_pf(const odeu_plan& plan, const odeu_pf_io& io, cudaStream_t stream) 
 }
 
 template <class Ode>
+int launch_rhs(const odeu_plan& plan, long long B, double t, const double* x, const double* theta,
+               const double* theta_shared, double* dx, cudaStream_t stream) {
+  if (B <= 0 || !x || !dx) { set_error("odeu_ode_rhs: invalid argument"); return -1; }
+  RhsArgs<Ode::NP> a;
+  a.B = B; a.t = t; a.x = x; a.theta = theta; a.dx = dx;
+  for (int k = 0; k < Ode::NP; ++k) a.theta_shared[k] = theta_shared ? theta_shared[k] : plan.theta_default[k];
+  ode_rhs_kernel<Ode><<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(a);
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("odeu_ode_rhs: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
+template <class Ode>
 Launchers resolve_solver(int solver) {
   switch (solver) {
-    case ODEU_SOLVER_RKF45: return {&launch_ekf<Ode, TabRKF45>, &launch_pf<Ode, TabRKF45>};
-    case ODEU_SOLVER_DOPRI65: return {&launch_ekf<Ode, TabDopri65>, &launch_pf<Ode, TabDopri65>};
-    case ODEU_SOLVER_BS32: return {&launch_ekf<Ode, TabBS32>, &launch_pf<Ode, TabBS32>};
-    case ODEU_SOLVER_HEUN_EULER: return {&launch_ekf<Ode, TabHeunEuler>, &launch_pf<Ode, TabHeunEuler>};
-    default: return {nullptr, nullptr};
+    case ODEU_SOLVER_RKF45: return {&launch_ekf<Ode, TabRKF45>, &launch_pf<Ode, TabRKF45>, &launch_rhs<Ode>};
+    case ODEU_SOLVER_DOPRI65: return {&launch_ekf<Ode, TabDopri65>, &launch_pf<Ode, TabDopri65>, &launch_rhs<Ode>};
+    case ODEU_SOLVER_BS32: return {&launch_ekf<Ode, TabBS32>, &launch_pf<Ode, TabBS32>, &launch_rhs<Ode>};
+    case ODEU_SOLVER_HEUN_EULER: return {&launch_ekf<Ode, TabHeunEuler>, &launch_pf<Ode, TabHeunEuler>, &launch_rhs<Ode>};
+    default: return {nullptr, nullptr, nullptr};
   }
 }
 

@@ -63,6 +63,7 @@ struct PfArgs {
   double cov_scale;
   unsigned long long seed;
   long long particle_offset, step_offset, save_interval;
+  int noise_free;
   const double* x0;
   double* xT; double* epsT; double* tT; double* out_t; double* out_x; double* out_eps;
   double x0s[NX];
@@ -95,7 +96,7 @@ ODEU_HD void pf_particle(const PfArgs<Ode::NX, Ode::NP>& a, const long long m) {
     double xn[n];
     rk_step_plain<Ode, Tab>(t, a.h, x, th, xn, eps);
     t = t + a.h;
-    if (gid != 0) {
+    if (gid != 0 && !a.noise_free) {
       const unsigned long long gstep = (unsigned long long)(a.step_offset + step);
       if (a.cov_fn == COV_OUTER) {
         double z0, z1;
@@ -145,4 +146,28 @@ pf_thread_kernel(const __grid_constant__ PfArgs<Ode::NX, Ode::NP> a) {
   pf_particle<Ode, Tab>(a, m);
 }
 
+}  // namespace odeu
+
+namespace odeu {
+// dx/dt = f(t, x, theta) for a batch: the `ODE` callable of src/ode/ode.py:6-7.
+template <int NP>
+struct RhsArgs {
+  long long B;
+  double t;
+  const double* x; const double* theta; double* dx;
+  double theta_shared[NP];
+};
+template <class Ode>
+__global__ void __launch_bounds__(128) ode_rhs_kernel(const __grid_constant__ RhsArgs<Ode::NP> a) {
+  const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (b >= a.B) return;
+  double x[Ode::NX], dx[Ode::NX], th[Ode::NP];
+#pragma unroll
+  for (int i = 0; i < Ode::NX; ++i) x[i] = a.x[i * a.B + b];
+#pragma unroll
+  for (int k = 0; k < Ode::NP; ++k) th[k] = a.theta ? a.theta[k * a.B + b] : a.theta_shared[k];
+  Ode::rhs(a.t, x, th, dx);
+#pragma unroll
+  for (int i = 0; i < Ode::NX; ++i) a.dx[i * a.B + b] = dx[i];
+}
 }  // namespace odeu

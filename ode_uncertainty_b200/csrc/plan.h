@@ -16,6 +16,8 @@ struct odeu_plan {
   // launcher selected at plan creation (ode x solver)
   int (*ekf_launch)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);
   int (*pf_launch)(const odeu_plan&, const odeu_pf_io&, cudaStream_t);
+  int (*rhs_launch)(const odeu_plan&, long long, double, const double*, const double*, const double*,
+                    double*, cudaStream_t);
 };
 
 namespace odeu {
@@ -25,7 +27,9 @@ void count_launch();
 
 using EkfLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);
 using PfLaunchFn = int (*)(const odeu_plan&, const odeu_pf_io&, cudaStream_t);
-struct Launchers { EkfLaunchFn ekf; PfLaunchFn pf; };
+using RhsLaunchFn = int (*)(const odeu_plan&, long long, double, const double*, const double*,
+                           const double*, double*, cudaStream_t);
+struct Launchers { EkfLaunchFn ekf; PfLaunchFn pf; RhsLaunchFn rhs; };
 
 // One translation unit per ODE family instantiates its kernels and exposes a resolver.
 Launchers resolve_lorenz(int solver);

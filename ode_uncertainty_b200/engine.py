@@ -92,7 +92,7 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             correct_flags: Optional[torch.Tensor] = None,
             xy_index_map: Optional[torch.Tensor] = None, save_interval: int = 0,
             save_keys=("t", "x", "eps", "P", "y_hat", "S"), want_final: bool = True,
-            stream: Optional[torch.cuda.Stream] = None) -> EkfResult:
+            skip_predict: bool = False, stream: Optional[torch.cuda.Stream] = None) -> EkfResult:
     """Run T EKF steps for a batch of trajectories.
 
     x0 [B, n] (CUDA, float64); P0 [B, n, n] per-trajectory covariance or P0_sqrt [n, n] shared
@@ -150,6 +150,7 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
     io.ys_per_trajectory = int(bool(ys_per_trajectory))
     io.correct_flags, io.xy_index_map = _dev(flags_k), _dev(map_k)
     io.save_interval = int(save_interval)
+    io.skip_predict = int(bool(skip_predict))
 
     xT = epsT = PT = yT = ST = None
     nll = torch.zeros(B, **f64)
@@ -216,7 +217,7 @@ class PfResult:
 
 def pf_run(plan: Plan, M: int, T: int, *, x0_shared=None, x0: Optional[torch.Tensor] = None,
            t0: float = 0.0, theta_shared=None, seed: int = 7, particle_offset: int = 0,
-           step_offset: int = 0, save_interval: int = 0, device=None,
+           step_offset: int = 0, save_interval: int = 0, device=None, noise_free: bool = False,
            stream: Optional[torch.cuda.Stream] = None) -> PfResult:
     """Perturbed-solver particle ensemble (src/filters/particle_filter.py:73-118), predict only."""
     n = plan.n
@@ -237,6 +238,7 @@ def pf_run(plan: Plan, M: int, T: int, *, x0_shared=None, x0: Optional[torch.Ten
     io.x0, io.x0_shared, io.theta_shared = _dev(x0_k), _hp(x0s_h), _hp(ths_h)
     io.seed, io.particle_offset, io.step_offset = int(seed), int(particle_offset), int(step_offset)
     io.save_interval = int(save_interval)
+    io.noise_free = int(bool(noise_free))
     xT = torch.empty(n, M, **f64)
     epsT = torch.empty(n, M, **f64)
     tT = torch.zeros(1, **f64)

@@ -148,8 +148,7 @@ def pow(a, b):
 
 
 def where(c, a, b):
-    return torch.where(c, _t(a, torch.float64) if not isinstance(a, torch.Tensor) else a,
-                       _t(b, torch.float64) if not isinstance(b, torch.Tensor) else b)
+    return torch.where(c, a, b)      # python scalars promote like jnp.where (ints stay ints)
 
 
 def sum(x, axis=None):

@@ -154,10 +154,31 @@ def run_nll_and_grad(spec):
                 lo=ravel_pytree(lo)[0].numpy(), hi=ravel_pytree(hi)[0].numpy())
 
 
+def sync_times_fixture():
+    """The reference's own sync_times (src/utils.py:181-215) on the float aranges its scripts
+    build (scripts/run_filter.py:99-105) for a few observation cadences."""
+    from src.utils import sync_times
+    out = {}
+    for tag, (t0, tN, h, dt_y) in {"every1": (0.0, 2.0, 0.01, 0.01), "every3": (0.0, 2.0, 0.01, 0.03),
+                                   "hh": (0.0, 100.0, 0.01, 0.01), "offset": (10.0, 12.0, 0.01, 0.05)}.items():
+        ts_y = jnp.arange(t0, tN + 1e-9, dt_y)
+        ts_x = jnp.arange(t0 + h, tN + h, h)
+        xi, yi = sync_times(ts_x, ts_y)
+        out[f"{tag}_args"] = np.array([t0, tN, h, dt_y])
+        out[f"{tag}_x"] = xi.numpy()
+        out[f"{tag}_y"] = yi.numpy()
+        out[f"{tag}_nx"] = np.array(ts_x.shape[0])
+    np.savez_compressed(os.path.join(cases.GOLDEN, "ref_sync_times.npz"), **out)
+    print("sync_times fixture:", {k: v.shape for k, v in out.items() if k.endswith("_x")})
+
+
 GRAD_CASES = ["lv_rkf45_temper_q_only", "lv_rkf45_temper_eps_plus_q", "hh_r4_rkf45_temper"]
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(cases.CASES)
+    if not sys.argv[1:] or "sync_times" in names:
+        sync_times_fixture()
+        names = [n for n in names if n != "sync_times"]
     for name in names:
         spec = cases.CASES[name]
         out = run_case(spec)

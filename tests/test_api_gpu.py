@@ -96,7 +96,8 @@ def test_solver_step_and_ode_rhs_match_oracle():
                                       "HodgkinHuxley/reduced-4": "hh_r4_rkf45_temper"}[name]]["x0"]).reshape(shape)
         f = b.build()
         got = f(12.0, x.to(dev), b.params).cpu()
-        np.testing.assert_allclose(got.numpy(), ode(torch.tensor(12.0), x, params).numpy(), rtol=1e-13, atol=1e-300)
+        # gate derivatives vanish at the HH steady state: compare against the size of the terms (O(1))
+        np.testing.assert_allclose(got.numpy(), ode(torch.tensor(12.0), x, params).numpy(), rtol=1e-12, atol=1e-15)
         for cls in (S.RKF45, S.Dopri65, S.BS32, S.HeunEuler):
             sb = cls(step_size=0.01)
             sb.setup(f, b.params)

@@ -130,6 +130,24 @@ typedef struct {
  * (scripts/run_parameter_estimation.py:771-794).  `cuda_stream` is a cudaStream_t. */
 int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream);
 
+/* NLL and its parameter gradient for B parameter sets: replaces jax.value_and_grad(nll) as the
+ * optimiser calls it (scripts/run_parameter_estimation.py:599, nll :685-796).  Forward-mode
+ * tangents over the requested parameters (at most 32), fused with the filter loop.  Uses from
+ * `io`: B, T, t0, L, x0, P0_sqrt, theta / theta_shared, Q_sqrt, gamma_sqrt, H, R_sqrt, ys,
+ * ys_per_trajectory, correct_flags, xy_index_map; writes io->nll [B], io->xT [n][B] (optional)
+ * and grad->grad.  The derivative is w.r.t. the PHYSICAL parameter theta_j; the caller applies
+ * d theta / d theta_norm = (max - min) (src/utils.py:156-178). */
+typedef struct {
+  int32_t p_opt;             /* number of differentiated parameters, 1..32 */
+  const int32_t* idx;        /* HOST [p_opt] flat parameter indices (ODEBuilder.params order) */
+  const double* x0_tangent;  /* DEVICE [p_opt][n][B] d x0 / d theta_j (initial_state_parametrized,
+                                run_parameter_estimation.py:744-748) or NULL = 0 */
+  double* grad;              /* DEVICE [p_opt][B] d NLL / d theta_j */
+} odeu_grad_io;
+
+int odeu_ekf_grad_run(const odeu_plan* plan, const odeu_ekf_io* io, const odeu_grad_io* grad,
+                      void* cuda_stream);
+
 /* Perturbed-solver particle ensemble (src/filters/particle_filter.py:24-118; Conrad et al.
  * baseline): M independent RK steps, after each step x += p with p ~ N(0, covfn(0, eps_m));
  * the particle with GLOBAL index 0 is noise-free (:104-105).  The reference draws from JAX's

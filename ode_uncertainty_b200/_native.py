@@ -21,6 +21,7 @@ SYMBOLS = (
     "odeu_version", "odeu_plan_create", "odeu_plan_destroy", "odeu_plan_state_dim",
     "odeu_plan_num_params", "odeu_plan_default_params", "odeu_ekf_run", "odeu_pf_run",
     "odeu_launch_count", "odeu_last_error", "odeu_bench_dfma", "odeu_ode_rhs",
+    "odeu_ekf_grad_run",
 )
 
 
@@ -46,6 +47,10 @@ class EkfIO(C.Structure):
         ("tT", _dp), ("out_t", _dp), ("out_x", _dp), ("out_eps", _dp), ("out_P", _dp),
         ("out_yhat", _dp), ("out_S", _dp),
     ]
+
+
+class GradIO(C.Structure):
+    _fields_ = [("p_opt", C.c_int32), ("idx", _dp), ("x0_tangent", _dp), ("grad", _dp)]
 
 
 class PfIO(C.Structure):
@@ -88,6 +93,8 @@ def lib() -> C.CDLL:
     L.odeu_bench_dfma.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                   C.POINTER(C.c_double), C.c_void_p]
     L.odeu_bench_dfma.restype = C.c_int
+    L.odeu_ekf_grad_run.argtypes = [C.c_void_p, C.POINTER(EkfIO), C.POINTER(GradIO), C.c_void_p]
+    L.odeu_ekf_grad_run.restype = C.c_int
     L.odeu_ode_rhs.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]
     L.odeu_ode_rhs.restype = C.c_int

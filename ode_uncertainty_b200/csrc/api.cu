@@ -104,6 +104,10 @@ int odeu_plan_create(const odeu_plan_desc* desc, odeu_plan** out) {
   p->ekf_launch = fn.ekf;
   p->pf_launch = fn.pf;
   p->rhs_launch = fn.rhs;
+  p->grad_launch = desc->ode_id == ODEU_ODE_HODGKIN_HUXLEY ? resolve_grad_hh(desc->ode_variant, desc->solver_id)
+                   : desc->ode_id == ODEU_ODE_MULTI_HH
+                       ? resolve_grad_multi_hh(desc->ode_variant, desc->num_compartments, desc->solver_id)
+                       : resolve_grad_small(desc->ode_id, desc->ode_variant, desc->solver_id);
   *out = p;
   return 0;
 }
@@ -126,6 +130,13 @@ int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream
 int odeu_pf_run(const odeu_plan* plan, const odeu_pf_io* io, void* cuda_stream) {
   if (!plan || !io) { set_error("odeu_pf_run: null argument"); return -1; }
   return plan->pf_launch(*plan, *io, (cudaStream_t)cuda_stream);
+}
+
+int odeu_ekf_grad_run(const odeu_plan* plan, const odeu_ekf_io* io, const odeu_grad_io* grad,
+                      void* cuda_stream) {
+  if (!plan || !io || !grad) { set_error("odeu_ekf_grad_run: null argument"); return -1; }
+  if (!plan->grad_launch) { set_error("odeu_ekf_grad_run: no gradient kernel for this plan"); return -2; }
+  return plan->grad_launch(*plan, *io, *grad, (cudaStream_t)cuda_stream);
 }
 
 int odeu_ode_rhs(const odeu_plan* plan, int64_t B, double t, const double* x, const double* theta,

@@ -1,0 +1,102 @@
+// Host launcher of the forward-mode gradient kernel (ekf_grad.cuh).
+#pragma once
+#include "ekf_grad.cuh"
+#include "plan.h"
+
+namespace odeu {
+
+template <class Ode>
+struct GradCfg {
+  static constexpr int KC = (Ode::NX <= 3) ? Ode::NX : ((Ode::NX == 4) ? 2 : 1);  // state columns / pass
+  static constexpr int PC = (Ode::NX <= 3) ? 2 : 1;                               // directions / thread
+  static constexpr int BLOCK = 64;
+};
+
+template <class Ode>
+int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g,
+                   GradArgs<Ode::NX, Ode::NP>& a) {
+  constexpr int n = Ode::NX;
+  constexpr int NP = Ode::NP;
+  if (io.B <= 0 || io.T < 0) { set_error("odeu_ekf_grad_run: B must be > 0 and T >= 0"); return -1; }
+  if (io.L < 0 || io.L > n) { set_error("odeu_ekf_grad_run: L=%d outside [0, n=%d]", io.L, n); return -1; }
+  if (!io.x0 || !io.P0_sqrt) { set_error("odeu_ekf_grad_run: x0 and a shared P0_sqrt are required"); return -1; }
+  if (io.P0) { set_error("odeu_ekf_grad_run: per-trajectory P0 is not supported"); return -1; }
+  if (g.p_opt < 1 || g.p_opt > ODEU_MAX_GRAD || !g.idx || !g.grad) {
+    set_error("odeu_ekf_grad_run: need 1..%d parameter indices and a grad buffer", ODEU_MAX_GRAD);
+    return -1;
+  }
+  if (io.L > 0 && (!io.H || !io.R_sqrt || !io.ys || !io.correct_flags || !io.xy_index_map)) {
+    set_error("odeu_ekf_grad_run: L > 0 needs H, R_sqrt, ys, correct_flags, xy_index_map");
+    return -1;
+  }
+  a.B = io.B; a.T = io.T; a.t0 = io.t0; a.h = plan.desc.step_size; a.L = io.L;
+  a.cov_fn = plan.desc.cov_fn_id; a.cov_scale = plan.desc.cov_scale;
+  a.ys_per_traj = io.ys_per_trajectory; a.has_obs = io.L > 0 ? 1 : 0;
+  a.p_opt = g.p_opt;
+  for (int j = 0; j < ODEU_MAX_GRAD; ++j) a.idx[j] = -1;
+  for (int j = 0; j < g.p_opt; ++j) {
+    if (g.idx[j] < 0 || g.idx[j] >= NP) { set_error("odeu_ekf_grad_run: parameter index %d out of range", g.idx[j]); return -1; }
+    a.idx[j] = g.idx[j];
+  }
+  a.x0 = io.x0; a.x0_tan = g.x0_tangent; a.theta = io.theta; a.ys = io.ys;
+  a.flags = io.correct_flags; a.ymap = (const long long*)io.xy_index_map;
+  a.nll = io.nll; a.grad = g.grad; a.xT = io.xT;
+  for (int i = 0; i < n * n; ++i) { a.P0s[i] = 0.0; a.GQ[i] = 0.0; a.H[i] = 0.0; a.R[i] = 0.0; }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s += io.P0_sqrt[i * n + k] * io.P0_sqrt[j * n + k];
+      a.P0s[i * n + j] = s;
+    }
+  bool qany = false;
+  if (io.Q_sqrt) {
+    for (int i = 0; i < n * n; ++i) qany = qany || (io.Q_sqrt[i] >= 1e-16);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k)
+          s += (io.gamma_sqrt * io.Q_sqrt[i * n + k]) * (io.gamma_sqrt * io.Q_sqrt[j * n + k]);
+        a.GQ[i * n + j] = s;
+      }
+  }
+  a.noise_mode = plan.desc.disable_cov_update ? (qany ? NOISE_Q_ONLY : NOISE_NONE)
+                                              : (qany ? NOISE_EPS_PLUS_Q : NOISE_COVFN);
+  for (int l = 0; l < io.L; ++l) {
+    for (int j = 0; j < n; ++j) a.H[l * n + j] = io.H[l * n + j];
+    for (int m = 0; m < io.L; ++m) {
+      double s = 0.0;
+      for (int k = 0; k < io.L; ++k) s += io.R_sqrt[l * io.L + k] * io.R_sqrt[m * io.L + k];
+      a.R[l * io.L + m] = s;
+    }
+  }
+  for (int k = 0; k < NP; ++k)
+    a.theta_shared[k] = io.theta_shared ? io.theta_shared[k] : plan.theta_default[k];
+  return 0;
+}
+
+template <class Ode, class Tab>
+int launch_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g, cudaStream_t stream) {
+  using Cfg = GradCfg<Ode>;
+  GradArgs<Ode::NX, Ode::NP> a;
+  if (int rc = fill_grad_args<Ode>(plan, io, g, a)) return rc;
+  const int nchunks = (g.p_opt + Cfg::PC - 1) / Cfg::PC;
+  dim3 grid((unsigned)((io.B + Cfg::BLOCK - 1) / Cfg::BLOCK), (unsigned)nchunks);
+  ekf_grad_kernel<Ode, Tab, Cfg::KC, Cfg::PC, Cfg::BLOCK><<<grid, Cfg::BLOCK, 0, stream>>>(a);
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("odeu_ekf_grad_run: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
+template <class Ode>
+GradLaunchFn resolve_grad_solver(int solver) {
+  switch (solver) {
+    case ODEU_SOLVER_RKF45: return &launch_grad<Ode, TabRKF45>;
+    case ODEU_SOLVER_DOPRI65: return &launch_grad<Ode, TabDopri65>;
+    case ODEU_SOLVER_BS32: return &launch_grad<Ode, TabBS32>;
+    case ODEU_SOLVER_HEUN_EULER: return &launch_grad<Ode, TabHeunEuler>;
+    default: return nullptr;
+  }
+}
+
+}  // namespace odeu

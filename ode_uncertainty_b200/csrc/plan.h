@@ -18,6 +18,7 @@ struct odeu_plan {
   int (*pf_launch)(const odeu_plan&, const odeu_pf_io&, cudaStream_t);
   int (*rhs_launch)(const odeu_plan&, long long, double, const double*, const double*, const double*,
                     double*, cudaStream_t);
+  int (*grad_launch)(const odeu_plan&, const odeu_ekf_io&, const odeu_grad_io&, cudaStream_t);
 };
 
 namespace odeu {
@@ -29,6 +30,10 @@ using EkfLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);
 using PfLaunchFn = int (*)(const odeu_plan&, const odeu_pf_io&, cudaStream_t);
 using RhsLaunchFn = int (*)(const odeu_plan&, long long, double, const double*, const double*,
                            const double*, double*, cudaStream_t);
+using GradLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, const odeu_grad_io&, cudaStream_t);
+GradLaunchFn resolve_grad_small(int ode_id, int variant, int solver);
+GradLaunchFn resolve_grad_hh(int model, int solver);
+GradLaunchFn resolve_grad_multi_hh(int model, int nc, int solver);
 struct Launchers { EkfLaunchFn ekf; PfLaunchFn pf; RhsLaunchFn rhs; };
 
 // One translation unit per ODE family instantiates its kernels and exposes a resolver.

@@ -207,6 +207,65 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
         ST=None if ST is None else ST.t().reshape(B, L, L), traj=traj)
 
 
+def ekf_grad_run(plan: Plan, x0: torch.Tensor, T: int, grad_idx, *, t0: float = 0.0, P0_sqrt=None,
+                 theta: Optional[torch.Tensor] = None, theta_shared=None, Q_sqrt=None,
+                 gamma_sqrt: float = 0.0, H=None, R_sqrt=None, ys: Optional[torch.Tensor] = None,
+                 ys_per_trajectory: bool = False, correct_flags: Optional[torch.Tensor] = None,
+                 xy_index_map: Optional[torch.Tensor] = None, x0_tangent: Optional[torch.Tensor] = None,
+                 stream: Optional[torch.cuda.Stream] = None):
+    """NLL [B] and d NLL / d theta_j [B, p_opt] for the flat parameter indices `grad_idx`
+    (builder order) in one launch (`odeu_ekf_grad_run`).  x0_tangent [B, p_opt, n] optional."""
+    _require_cuda(x0, "x0")
+    dev = x0.device
+    B, n = x0.shape
+    if n != plan.n:
+        raise ValueError(f"x0 has state dimension {n}, plan expects {plan.n}")
+    f64 = dict(dtype=torch.float64, device=dev)
+    idx = np.ascontiguousarray(np.asarray(grad_idx, dtype=np.int32))
+    p_opt = idx.size
+    x0_k = x0.to(torch.float64).t().contiguous()
+    P0s_h = _host(P0_sqrt, (n, n)) if P0_sqrt is not None else np.eye(n) * 1e-12
+    th_k = None
+    if theta is not None:
+        _require_cuda(theta, "theta")
+        th_k = theta.to(torch.float64).t().contiguous()
+    ths_h = _host(theta_shared, (plan.p,)) if theta_shared is not None else None
+    Q_h = _host(Q_sqrt, (n, n)) if Q_sqrt is not None else None
+    L = 0
+    H_h = R_h = None
+    ys_k = flags_k = map_k = None
+    if H is not None and ys is not None:
+        H_h = _host(H)
+        L = H_h.shape[0]
+        R_h = _host(R_sqrt, (L, L))
+        _require_cuda(ys, "ys")
+        ys_k = (ys.to(torch.float64).permute(0, 2, 1).contiguous() if ys_per_trajectory
+                else ys.to(torch.float64).reshape(-1, L).contiguous())
+        flags_k = correct_flags.to(device=dev, dtype=torch.uint8).contiguous()
+        map_k = xy_index_map.to(device=dev, dtype=torch.int64).contiguous()
+    x0t_k = None
+    if x0_tangent is not None:
+        x0t_k = x0_tangent.to(torch.float64).permute(1, 2, 0).contiguous()    # [p_opt][n][B]
+    io = N.EkfIO()
+    io.B, io.T, io.t0, io.L = B, int(T), float(t0), L
+    io.x0, io.P0_sqrt = _dev(x0_k), _hp(P0s_h)
+    io.theta, io.theta_shared = _dev(th_k), _hp(ths_h)
+    io.Q_sqrt, io.gamma_sqrt = _hp(Q_h), float(gamma_sqrt)
+    io.H, io.R_sqrt, io.ys = _hp(H_h), _hp(R_h), _dev(ys_k)
+    io.ys_per_trajectory = int(bool(ys_per_trajectory))
+    io.correct_flags, io.xy_index_map = _dev(flags_k), _dev(map_k)
+    nll = torch.zeros(B, **f64)
+    grad = torch.zeros(p_opt, B, **f64)
+    io.nll = _dev(nll)
+    g = N.GradIO()
+    g.p_opt, g.idx, g.x0_tangent, g.grad = int(p_opt), idx.ctypes.data_as(C.c_void_p), _dev(x0t_k), _dev(grad)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().odeu_ekf_grad_run(plan.handle, C.byref(io), C.byref(g), C.c_void_p(st.cuda_stream)),
+                "odeu_ekf_grad_run")
+    return nll, grad.t()
+
+
 @dataclass
 class PfResult:
     xT: torch.Tensor       # [M, n]

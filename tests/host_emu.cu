@@ -5,6 +5,7 @@
 // against the oracle in a container without a GPU.  All pointers of the io structs are HOST
 // pointers here.  The shipped library has no such entry point.
 #include "../ode_uncertainty_b200/csrc/launch.cuh"
+#include "../ode_uncertainty_b200/csrc/launch_grad.cuh"
 
 namespace odeu {
 static thread_local std::string g_err;
@@ -43,8 +44,21 @@ int emu_pf(const odeu_plan& plan, const odeu_pf_io& io) {
   return 0;
 }
 
+// host replay of launch_grad: same argument folding, then the per-(trajectory, chunk) body
+template <class Ode, class Tab>
+int emu_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g);
+
 template <class Ode>
-int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p) {
+int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p, const odeu_grad_io* g = nullptr) {
+  if (g) {
+    switch (plan.desc.solver_id) {
+      case ODEU_SOLVER_RKF45: return emu_grad<Ode, TabRKF45>(plan, *e, *g);
+      case ODEU_SOLVER_DOPRI65: return emu_grad<Ode, TabDopri65>(plan, *e, *g);
+      case ODEU_SOLVER_BS32: return emu_grad<Ode, TabBS32>(plan, *e, *g);
+      case ODEU_SOLVER_HEUN_EULER: return emu_grad<Ode, TabHeunEuler>(plan, *e, *g);
+    }
+    return -2;
+  }
   switch (plan.desc.solver_id) {
     case ODEU_SOLVER_RKF45: return e ? emu_ekf<Ode, TabRKF45>(plan, *e) : emu_pf<Ode, TabRKF45>(plan, *p);
     case ODEU_SOLVER_DOPRI65: return e ? emu_ekf<Ode, TabDopri65>(plan, *e) : emu_pf<Ode, TabDopri65>(plan, *p);
@@ -55,31 +69,49 @@ int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p)
 }
 
 static int emu_dispatch(const odeu_plan_desc& d, const double* theta_default, int p,
-                        const odeu_ekf_io* e, const odeu_pf_io* pf) {
+                        const odeu_ekf_io* e, const odeu_pf_io* pf, const odeu_grad_io* g = nullptr) {
   odeu_plan plan;
   plan.desc = d;
   plan.theta_default.assign(theta_default, theta_default + p);
   switch (d.ode_id) {
-    case ODEU_ODE_LORENZ: return emu_solver<OdeLorenz>(plan, e, pf);
-    case ODEU_ODE_VAN_DER_POL: return emu_solver<OdeVanDerPol>(plan, e, pf);
-    case ODEU_ODE_LOTKA_VOLTERRA: return emu_solver<OdeLotkaVolterra>(plan, e, pf);
-    case ODEU_ODE_PENDULUM: return emu_solver<OdePendulum>(plan, e, pf);
-    case ODEU_ODE_LCAO: if (d.ode_variant == 2) return emu_solver<OdeLCAO<2>>(plan, e, pf); break;
+    case ODEU_ODE_LORENZ: return emu_solver<OdeLorenz>(plan, e, pf, g);
+    case ODEU_ODE_VAN_DER_POL: return emu_solver<OdeVanDerPol>(plan, e, pf, g);
+    case ODEU_ODE_LOTKA_VOLTERRA: return emu_solver<OdeLotkaVolterra>(plan, e, pf, g);
+    case ODEU_ODE_PENDULUM: return emu_solver<OdePendulum>(plan, e, pf, g);
+    case ODEU_ODE_LCAO: if (d.ode_variant == 2) return emu_solver<OdeLCAO<2>>(plan, e, pf, g); break;
     case ODEU_ODE_HODGKIN_HUXLEY:
-      if (d.ode_variant == 0) return emu_solver<OdeHodgkinHuxley<0>>(plan, e, pf);
-      if (d.ode_variant == 1) return emu_solver<OdeHodgkinHuxley<1>>(plan, e, pf);
-      if (d.ode_variant == 4) return emu_solver<OdeHodgkinHuxley<4>>(plan, e, pf);
+      if (d.ode_variant == 0) return emu_solver<OdeHodgkinHuxley<0>>(plan, e, pf, g);
+      if (d.ode_variant == 1) return emu_solver<OdeHodgkinHuxley<1>>(plan, e, pf, g);
+      if (d.ode_variant == 4) return emu_solver<OdeHodgkinHuxley<4>>(plan, e, pf, g);
       break;
     case ODEU_ODE_MULTI_HH:
-      if (d.num_compartments == 2 && d.ode_variant == 1) return emu_solver<OdeMultiHH<1, 2>>(plan, e, pf);
-      if (d.num_compartments == 2 && d.ode_variant == 4) return emu_solver<OdeMultiHH<4, 2>>(plan, e, pf);
+      if (d.num_compartments == 2 && d.ode_variant == 1) return emu_solver<OdeMultiHH<1, 2>>(plan, e, pf, g);
+      if (d.num_compartments == 2 && d.ode_variant == 4) return emu_solver<OdeMultiHH<4, 2>>(plan, e, pf, g);
       break;
   }
   return -2;
 }
+
+// The gradient launcher normally launches a kernel; for the emulation the kernel launch is
+// replaced by a host loop over (trajectory, chunk).  launch_grad's argument folding is reused by
+// intercepting the arguments it builds: we re-run its validation through a host-only copy.
+template <class Ode, class Tab>
+int emu_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g) {
+  GradArgs<Ode::NX, Ode::NP> a;
+  if (int rc = fill_grad_args<Ode>(plan, io, g, a)) return rc;
+  using Cfg = GradCfg<Ode>;
+  const int nchunks = (g.p_opt + Cfg::PC - 1) / Cfg::PC;
+  for (int c = 0; c < nchunks; ++c)
+    for (long long b = 0; b < io.B; ++b) ekf_grad_trajectory<Ode, Tab, Cfg::KC, Cfg::PC>(a, b, c);
+  return 0;
+}
 }  // namespace odeu
 
 extern "C" {
+int hostemu_grad_run(const odeu_plan_desc* d, const double* theta_default, int p, const odeu_ekf_io* io,
+                     const odeu_grad_io* g) {
+  return odeu::emu_dispatch(*d, theta_default, p, io, nullptr, g);
+}
 int hostemu_ekf_run(const odeu_plan_desc* d, const double* theta_default, int p, const odeu_ekf_io* io) {
   return odeu::emu_dispatch(*d, theta_default, p, io, nullptr);
 }

@@ -1,0 +1,69 @@
+"""Forward-mode NLL gradients of the kernel source (host-compiled) against
+  (a) the reference's own reverse-mode gradient: jax.value_and_grad over the reference's nll()
+      (scripts/run_parameter_estimation.py:685-796) executed over the jax look-alike
+      (tests/golden/ref_*.npz: grad_norm, sorted-key order, w.r.t. normalised parameters), and
+  (b) central finite differences of the kernel's own NLL.
+Tolerance: 1e-6 relative on gradients."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import util as U
+from ode_uncertainty_b200 import ode as O
+from ode_uncertainty_b200 import runners
+
+REF_GRAD = {"lv_rkf45_temper_q_only": O.LotkaVolterra, "lv_rkf45_temper_eps_plus_q": O.LotkaVolterra,
+            "hh_r4_rkf45_temper": lambda: O.HodgkinHuxley(model="reduced-4")}
+
+
+def _run(backend, name, theta_sorted=None):
+    spec = cases.CASES[name]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    ob = REF_GRAD[name]()
+    keys_s, sizes, perm = runners.param_layout(ob)
+    inv = np.argsort(perm)                       # builder index of each sorted-order entry
+    default_sorted = np.concatenate([ob.params[k].reshape(-1) for k in keys_s])
+    ths = default_sorted if theta_sorted is None else theta_sorted
+    # differentiate every parameter, requested in sorted-key order
+    idx_builder = np.array([int(np.nonzero(perm == j)[0][0]) for j in range(perm.size)])
+    nll, g = U.run_grad(backend, plan, m["x0"].reshape(1, -1).numpy(), m["T"], idx_builder, t0=m["t0"],
+                        P0_sqrt=m["P0s"].numpy(), theta_shared=ths[perm], Q_sqrt=m["Q"].numpy(),
+                        gamma_sqrt=m["gamma"] ** 0.5, H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(),
+                        ys=m["ys"].numpy(), correct_flags=m["flags"], xy_index_map=m["ymap"])
+    return nll[0], g[0], default_sorted
+
+
+@pytest.mark.parametrize("name", list(REF_GRAD))
+def test_forward_mode_gradient_matches_reference_reverse_mode(name):
+    ref = dict(np.load(os.path.join(cases.GOLDEN, f"ref_{name}.npz")))
+    nll, g, _ = _run("hostemu", name)
+    assert abs(nll - float(ref["nll_fn"])) <= 1e-9 * abs(float(ref["nll_fn"]))
+    g_norm = g * (ref["hi"] - ref["lo"])          # d/d theta_norm = d/d theta * (max - min)
+    scale = np.max(np.abs(ref["grad_norm"]))
+    np.testing.assert_allclose(g_norm, ref["grad_norm"], rtol=1e-6, atol=1e-6 * scale)
+
+
+def test_gradient_matches_finite_differences_lorenz_eps_branch():
+    """Lorenz, eps enters P (NOISE_COVFN): d eps/d theta via sign(x0 - x1)."""
+    spec = cases.CASES["lorenz_rkf45_obs_full"]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    kw = dict(t0=m["t0"], P0_sqrt=np.eye(3) * 1e-2, H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(),
+              ys=m["ys"].numpy()[:40], correct_flags=m["flags"][:40], xy_index_map=m["ymap"][:40])
+    x0 = m["x0"].reshape(1, -1).numpy()
+    th = plan.default_params.copy()
+    nll, g = U.run_grad("hostemu", plan, x0, 40, [0, 1, 2], theta_shared=th, **kw)
+    for j in range(3):
+        d = 1e-6 * abs(th[j])
+        tp, tm = th.copy(), th.copy()
+        tp[j] += d
+        tm[j] -= d
+        fp = U.run_ekf("hostemu", plan, x0, 40, theta_shared=tp, **kw)["nll"][0]
+        fm = U.run_ekf("hostemu", plan, x0, 40, theta_shared=tm, **kw)["nll"][0]
+        fd = (fp - fm) / (2 * d)
+        assert abs(g[0, j] - fd) <= 2e-5 * max(1.0, abs(fd)), (j, g[0, j], fd)
+    base = U.run_ekf("hostemu", plan, x0, 40, theta_shared=th, **kw)["nll"][0]
+    assert abs(nll[0] - base) <= 1e-10 * abs(base)

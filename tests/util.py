@@ -44,6 +44,8 @@ def hostemu():
                                          C.POINTER(N.EkfIO)]
         _emu.hostemu_pf_run.argtypes = [C.POINTER(N.PlanDesc), C.POINTER(C.c_double), C.c_int,
                                         C.POINTER(N.PfIO)]
+        _emu.hostemu_grad_run.argtypes = [C.POINTER(N.PlanDesc), C.POINTER(C.c_double), C.c_int,
+                                          C.POINTER(N.EkfIO), C.POINTER(N.GradIO)]
         _emu.hostemu_last_error.restype = C.c_char_p
     return _emu
 
@@ -206,3 +208,59 @@ def rel_err(a, b, floor=0.0):
     if scale == 0:
         return float(np.max(np.abs(a - b)))
     return float(np.max(np.abs(a - b)) / scale)
+
+
+def run_grad(backend, plan, x0, T, grad_idx, *, t0=0.0, P0_sqrt=None, theta=None, theta_shared=None,
+             Q_sqrt=None, gamma_sqrt=0.0, H=None, R_sqrt=None, ys=None, correct_flags=None,
+             xy_index_map=None):
+    """Returns (nll [B], grad [B, p_opt]) from the product path (gpu) or the host-compiled source."""
+    x0 = _np(x0)
+    B, n = x0.shape
+    if backend == "gpu":
+        from ode_uncertainty_b200 import ekf_grad_run
+        dev = torch.device("cuda:0")
+        tt = lambda a, dt=torch.float64: None if a is None else torch.as_tensor(np.asarray(a), dtype=dt).to(dev)
+        nll, g = ekf_grad_run(plan, tt(x0), T, grad_idx, t0=t0, P0_sqrt=P0_sqrt, theta=tt(theta),
+                              theta_shared=theta_shared, Q_sqrt=Q_sqrt, gamma_sqrt=gamma_sqrt, H=H,
+                              R_sqrt=R_sqrt, ys=tt(ys), correct_flags=tt(correct_flags, torch.uint8),
+                              xy_index_map=tt(xy_index_map, torch.int64))
+        torch.cuda.synchronize()
+        return nll.cpu().numpy(), g.cpu().numpy()
+    emu = hostemu()
+    keep = []
+
+    def K(a):
+        keep.append(a)
+        return a
+
+    io = N.EkfIO()
+    io.B, io.T, io.t0 = B, int(T), float(t0)
+    io.x0 = _p(K(np.ascontiguousarray(x0.T)))
+    io.P0_sqrt = _p(K(np.eye(n) * 1e-12 if P0_sqrt is None else _np(P0_sqrt).reshape(n, n)))
+    if theta is not None:
+        io.theta = _p(K(np.ascontiguousarray(_np(theta).T)))
+    if theta_shared is not None:
+        io.theta_shared = _p(K(_np(theta_shared)))
+    if Q_sqrt is not None:
+        io.Q_sqrt = _p(K(_np(Q_sqrt).reshape(n, n)))
+    io.gamma_sqrt = float(gamma_sqrt)
+    L = 0
+    if H is not None and ys is not None:
+        Hn = K(_np(H))
+        L = Hn.shape[0]
+        io.H = _p(Hn)
+        io.R_sqrt = _p(K(_np(R_sqrt).reshape(L, L)))
+        io.ys = _p(K(_np(ys)))
+        io.correct_flags = _p(K(_np(correct_flags, np.uint8)))
+        io.xy_index_map = _p(K(_np(xy_index_map, np.int64)))
+    io.L = L
+    idx = K(np.ascontiguousarray(np.asarray(grad_idx, dtype=np.int32)))
+    nll, grad = np.zeros(B), np.zeros((idx.size, B))
+    io.nll = _p(nll)
+    g = N.GradIO()
+    g.p_opt, g.idx, g.grad = int(idx.size), _p(idx), _p(grad)
+    th = (C.c_double * plan.p)(*plan.default_params)
+    rc = emu.hostemu_grad_run(C.byref(plan.desc), th, plan.p, C.byref(io), C.byref(g))
+    if rc != 0:
+        raise ValueError(f"hostemu: {emu.hostemu_last_error().decode()} ({rc})")
+    return nll, grad.T.copy()

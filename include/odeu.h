@@ -110,6 +110,10 @@ typedef struct {
   int64_t save_interval;     /* 0 = no trajectory output; else slots 0, s, 2s, ... (run_filter.py:219-222) */
   int32_t skip_predict;      /* 1: apply only the measurement update in each step (single-step
                                 FilterCorrect of src/filters/filter.py:31-33; API-compat/tests) */
+  void* workspace;           /* DEVICE scratch of odeu_ekf_workspace_bytes() bytes, or NULL.  When
+                                given (and save_interval == 0, B large) the run is scheduled
+                                dynamically over (trajectory block, time segment) work items */
+  int64_t workspace_bytes;
   /* ---- outputs (DEVICE, any may be NULL) */
   double* xT;                /* [n][B]    final mean */
   double* epsT;              /* [n][B]    last local error estimate */
@@ -125,6 +129,9 @@ typedef struct {
   double* out_yhat;          /* [T_save][L][B] */
   double* out_S;             /* [T_save][L*L][B] */
 } odeu_ekf_io;
+
+/* Scratch size for the dynamically scheduled variant of odeu_ekf_run (0 if it does not apply). */
+int64_t odeu_ekf_workspace_bytes(const odeu_plan* plan, int64_t B, int64_t T);
 
 /* Replaces unroll() (scripts/run_filter.py:166-224) and the scan of nll()
  * (scripts/run_parameter_estimation.py:771-794).  `cuda_stream` is a cudaStream_t. */

@@ -21,7 +21,7 @@ SYMBOLS = (
     "odeu_version", "odeu_plan_create", "odeu_plan_destroy", "odeu_plan_state_dim",
     "odeu_plan_num_params", "odeu_plan_default_params", "odeu_ekf_run", "odeu_pf_run",
     "odeu_launch_count", "odeu_last_error", "odeu_bench_dfma", "odeu_ode_rhs",
-    "odeu_ekf_grad_run",
+    "odeu_ekf_grad_run", "odeu_ekf_workspace_bytes",
 )
 
 
@@ -42,7 +42,8 @@ class EkfIO(C.Structure):
         ("x0", _dp), ("P0", _dp), ("P0_sqrt", _dp), ("theta", _dp), ("theta_shared", _dp),
         ("Q_sqrt", _dp), ("gamma_sqrt", C.c_double), ("H", _dp), ("R_sqrt", _dp), ("ys", _dp),
         ("ys_per_trajectory", C.c_int32), ("correct_flags", _dp), ("xy_index_map", _dp),
-        ("save_interval", C.c_int64), ("skip_predict", C.c_int32),
+        ("save_interval", C.c_int64), ("skip_predict", C.c_int32), ("workspace", _dp),
+        ("workspace_bytes", C.c_int64),
         ("xT", _dp), ("epsT", _dp), ("PT", _dp), ("yhatT", _dp), ("ST", _dp), ("nll", _dp),
         ("tT", _dp), ("out_t", _dp), ("out_x", _dp), ("out_eps", _dp), ("out_P", _dp),
         ("out_yhat", _dp), ("out_S", _dp),
@@ -93,6 +94,8 @@ def lib() -> C.CDLL:
     L.odeu_bench_dfma.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                   C.POINTER(C.c_double), C.c_void_p]
     L.odeu_bench_dfma.restype = C.c_int
+    L.odeu_ekf_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    L.odeu_ekf_workspace_bytes.restype = C.c_int64
     L.odeu_ekf_grad_run.argtypes = [C.c_void_p, C.POINTER(EkfIO), C.POINTER(GradIO), C.c_void_p]
     L.odeu_ekf_grad_run.restype = C.c_int
     L.odeu_ode_rhs.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,

@@ -63,6 +63,9 @@ static bool default_params(const odeu_plan_desc& d, int* n, std::vector<double>*
 
 using namespace odeu;
 
+// defined in k_lorenz.cu (needs the launcher header)
+long long odeu_sched_bytes(int n, long long B, long long T);
+
 extern "C" {
 
 int odeu_version(void) { return ODEU_VERSION; }
@@ -120,6 +123,11 @@ int odeu_plan_default_params(const odeu_plan* plan, double* out) {
   if (!plan || !out) { set_error("odeu_plan_default_params: null argument"); return -1; }
   std::memcpy(out, plan->theta_default.data(), sizeof(double) * plan->p);
   return 0;
+}
+
+int64_t odeu_ekf_workspace_bytes(const odeu_plan* plan, int64_t B, int64_t T) {
+  if (!plan || B <= 0 || T <= 0) return 0;
+  return odeu_sched_bytes(plan->n, (long long)B, (long long)T);
 }
 
 int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream) {

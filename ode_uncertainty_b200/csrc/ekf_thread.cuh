@@ -80,8 +80,27 @@ ODEU_HD void save_slot(long long slot, long long B, long long b, int L,
 // ever calls it from the kernel below.
 // LK selects the measurement-update code at compile time: -1 = generic (run-time L, dense H),
 // 0 = prediction only, 1..n = H = [I_LK 0] (correct_step_lead).
+//
+// Time segments: the run may be cut into segments [step0, step1) executed by different warps
+// (dynamic scheduler below).  Between segments the per-trajectory state (x, P, nll; t per
+// 32-trajectory block) lives in the caller-provided workspace `ws`, laid out batch-minor like
+// every other array; it is read with L2-only loads because another SM wrote it.
+ODEU_HD double ws_load(const double* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+
+struct Segment {
+  long long step0, step1;   // steps of this segment
+  bool first, last;         // first: state comes from x0/P0/t0; last: final outputs are written
+  double* ws;               // [n + n*n + 1][B] state, then t per block of 32 trajectories
+};
+
 template <class Ode, class Tab, int KC, int LK>
-ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long b) {
+ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long b, const Segment& sg) {
   constexpr int n = Ode::NX;
   constexpr int NP = Ode::NP;
   constexpr int U = (n <= 4) ? n : 1;
@@ -89,33 +108,51 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   const int L = a.L;
 
   double x[n], eps[n], P[n][n], th[NP];
+  double t, nll;
+  if (sg.first) {
 #pragma unroll U
-  for (int i = 0; i < n; ++i) { x[i] = a.x0[i * B + b]; eps[i] = 0.0; }
+    for (int i = 0; i < n; ++i) x[i] = a.x0[i * B + b];
 #pragma unroll U
-  for (int i = 0; i < n; ++i)
+    for (int i = 0; i < n; ++i)
 #pragma unroll U
-    for (int j = 0; j < n; ++j) P[i][j] = a.P0 ? a.P0[(i * n + j) * B + b] : a.P0s[i * n + j];
-  // final-state y_hat / S start at zero like SQRT_EKF.init_state (sqrt_ekf.py:80-82)
-  for (int l = 0; l < L; ++l)
-    if (a.yhatT) a.yhatT[l * B + b] = 0.0;
-  for (int l = 0; l < L * L; ++l)
-    if (a.ST) a.ST[l * B + b] = 0.0;
+      for (int j = 0; j < n; ++j) P[i][j] = a.P0 ? a.P0[(i * n + j) * B + b] : a.P0s[i * n + j];
+    // final-state y_hat / S start at zero like SQRT_EKF.init_state (sqrt_ekf.py:80-82)
+    for (int l = 0; l < L; ++l)
+      if (a.yhatT) a.yhatT[l * B + b] = 0.0;
+    for (int l = 0; l < L * L; ++l)
+      if (a.ST) a.ST[l * B + b] = 0.0;
+    t = a.t0;
+    nll = 0.0;
+  } else {
+#pragma unroll U
+    for (int i = 0; i < n; ++i) x[i] = ws_load(sg.ws + i * B + b);
+#pragma unroll U
+    for (int i = 0; i < n; ++i)
+#pragma unroll U
+      for (int j = 0; j <= i; ++j) {
+        const double v = ws_load(sg.ws + (n + i * n + j) * B + b);
+        P[i][j] = v;
+        P[j][i] = v;
+      }
+    nll = ws_load(sg.ws + (n + n * n) * B + b);
+    t = ws_load(sg.ws + (n + n * n + 1) * B + (b >> 5));
+  }
+#pragma unroll U
+  for (int i = 0; i < n; ++i) eps[i] = 0.0;
   bool obs_fresh = false;
 #pragma unroll
   for (int k = 0; k < NP; ++k) th[k] = a.theta ? a.theta[k * B + b] : a.theta_shared[k];
 
-  double t = a.t0;
-  double nll = 0.0;
   const double h = a.h;
   const long long si = a.save_interval;
-  if (si > 0) {
+  if (si > 0 && sg.first) {
     save_slot<n>(0, B, b, L, x, eps, P, false, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
     if (b == 0 && a.out_t) a.out_t[0] = t;
   }
   long long next_save = si;  // step count at which the next slot is written
   long long slot = 1;
 
-  for (long long step = 0; step < a.T; ++step) {
+  for (long long step = sg.step0; step < sg.step1; ++step) {
     // ---- predict (src/filters/sqrt_ekf.py:92-197)
     double xn[n], J[n][n];
     if (LK == -1 && a.skip_predict) {
@@ -182,6 +219,17 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     }
   }
 
+  if (!sg.last) {   // hand the state to whoever runs the next segment
+#pragma unroll U
+    for (int i = 0; i < n; ++i) sg.ws[i * B + b] = x[i];
+#pragma unroll U
+    for (int i = 0; i < n; ++i)
+#pragma unroll U
+      for (int j = 0; j <= i; ++j) sg.ws[(n + i * n + j) * B + b] = P[i][j];
+    sg.ws[(n + n * n) * B + b] = nll;
+    if ((b & 31) == 0) sg.ws[(n + n * n + 1) * B + (b >> 5)] = t;
+    return;
+  }
   // ---- final state
 #pragma unroll U
   for (int i = 0; i < n; ++i) {
@@ -203,7 +251,63 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 ekf_thread_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a) {
   const long long b = (long long)blockIdx.x * BLOCK + threadIdx.x;
   if (b >= a.B) return;
-  ekf_trajectory<Ode, Tab, KC, LK>(a, b);
+  const Segment whole = {0, a.T, true, true, nullptr};
+  ekf_trajectory<Ode, Tab, KC, LK>(a, b, whole);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent, dynamically scheduled variant (throughput runs, save_interval == 0).
+//
+// Why: B = 65,536 trajectories are 2,048 warps, i.e. 3.46 per SM sub-partition; with one static
+// launch, sub-partitions holding 4 warps set the run time while those holding 3 idle for the
+// last quarter (ncu: smsp__inst_executed max/min = 4:3, profiles/r1a_*).  Here the run is cut
+// into (block of 32 trajectories) x (time segment) work items handed out through one global
+// counter in segment-major order; a warp that draws (block, s) waits until segment s-1 of that
+// block has been published (done[block] >= s), picks the state up from the workspace, runs the
+// segment and publishes it.  Every item only ever waits on an item that was handed out earlier
+// to a warp that is already running, so the scheme cannot deadlock whatever the residency.
+struct SchedArgs {
+  long long seg_len, nseg, nblk;
+  double* ws;                // state workspace (see Segment)
+  int* counter;              // next work item
+  int* done;                 // [nblk] number of published segments per block
+};
+
+template <class Ode, class Tab, int KC, int LK, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+ekf_thread_sched_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a,
+                        const __grid_constant__ SchedArgs s) {
+  const int lane = threadIdx.x & 31;
+  const long long total = s.nblk * s.nseg;
+  for (;;) {
+    long long item = 0;
+    if (lane == 0) item = atomicAdd(s.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) return;
+    const long long seg = item / s.nblk;
+    const long long blk = item % s.nblk;
+    if (seg > 0) {
+      if (lane == 0) {
+        volatile int* d = s.done + blk;
+        while (*d < (int)seg) __nanosleep(64);
+      }
+      __syncwarp();
+      __threadfence();
+    }
+    const long long b = blk * 32 + lane;
+    if (b < a.B) {
+      Segment sg;
+      sg.step0 = seg * s.seg_len;
+      sg.step1 = (seg + 1 == s.nseg) ? a.T : (seg + 1) * s.seg_len;
+      sg.first = seg == 0;
+      sg.last = seg + 1 == s.nseg;
+      sg.ws = s.ws;
+      ekf_trajectory<Ode, Tab, KC, LK>(a, b, sg);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(s.done + blk, (int)seg + 1);
+  }
 }
 
 }  // namespace odeu

@@ -103,12 +103,53 @@ int select_lk(const odeu_ekf_io& io) {
   return io.L;
 }
 
+// ---- dynamic (block, time-segment) scheduling: geometry shared by the size query and the launch
+struct SchedGeom {
+  long long seg_len, nseg, nblk, state_doubles, bytes;
+};
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+inline bool sched_geometry(int n, long long B, long long T, SchedGeom& g) {
+  g.nblk = (B + 31) / 32;
+  g.seg_len = (T + 47) / 48;
+  if (g.seg_len < 64) g.seg_len = 64;
+  g.nseg = (T + g.seg_len - 1) / g.seg_len;
+  g.state_doubles = (long long)(n + n * n + 1) * B + g.nblk;
+  g.bytes = g.state_doubles * 8 + (1 + g.nblk) * 4 + 64;
+  // worth it only when every SM sub-partition holds several warps and there are several segments
+  return n <= 4 && g.nseg >= 4 && g.nblk >= 4LL * 4 * sm_count();
+}
+
 template <class Ode, class Tab, int LK>
-void launch_ekf_variant(const EkfArgs<Ode::NX, Ode::NP>& a, cudaStream_t stream) {
+int launch_ekf_variant(const EkfArgs<Ode::NX, Ode::NP>& a, const odeu_ekf_io& io, cudaStream_t stream) {
   using Cfg = LaunchCfg<Ode>;
+  SchedGeom g;
+  if (io.workspace && io.save_interval == 0 && !io.skip_predict && sched_geometry(Ode::NX, a.B, a.T, g) &&
+      io.workspace_bytes >= g.bytes) {
+    SchedArgs s;
+    s.seg_len = g.seg_len; s.nseg = g.nseg; s.nblk = g.nblk;
+    s.ws = (double*)io.workspace;
+    s.counter = (int*)((char*)io.workspace + g.state_doubles * 8);
+    s.done = s.counter + 1;
+    cudaError_t e = cudaMemsetAsync(s.counter, 0, (1 + g.nblk) * 4, stream);
+    if (e != cudaSuccess) { set_error("odeu_ekf_run: workspace memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    const long long resident = (long long)sm_count() * Cfg::MINB;     // one CTA per register slot
+    ekf_thread_sched_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB>
+        <<<(unsigned)resident, Cfg::BLOCK, 0, stream>>>(a, s);
+    return 0;
+  }
   const long long grid = (a.B + Cfg::BLOCK - 1) / Cfg::BLOCK;
   ekf_thread_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB>
       <<<(unsigned)grid, Cfg::BLOCK, 0, stream>>>(a);
+  return 0;
 }
 
 template <class Ode, class Tab>
@@ -118,14 +159,16 @@ int launch_ekf(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream
   if (int rc = fill_ekf_args<Ode>(plan, io, a)) return rc;
   fill_scaled_tableau<Tab>(plan.desc.step_size, a.st);
   const int lk = select_lk<Ode>(io);
+  int rc = 0;
   if constexpr (n <= 4) {
-    if (lk == 0) launch_ekf_variant<Ode, Tab, 0>(a, stream);
-    else if (lk == 1) launch_ekf_variant<Ode, Tab, 1>(a, stream);
-    else if (lk == n) launch_ekf_variant<Ode, Tab, n>(a, stream);
-    else launch_ekf_variant<Ode, Tab, -1>(a, stream);
+    if (lk == 0) rc = launch_ekf_variant<Ode, Tab, 0>(a, io, stream);
+    else if (lk == 1) rc = launch_ekf_variant<Ode, Tab, 1>(a, io, stream);
+    else if (lk == n) rc = launch_ekf_variant<Ode, Tab, n>(a, io, stream);
+    else rc = launch_ekf_variant<Ode, Tab, -1>(a, io, stream);
   } else {
-    launch_ekf_variant<Ode, Tab, -1>(a, stream);
+    rc = launch_ekf_variant<Ode, Tab, -1>(a, io, stream);
   }
+  if (rc) return rc;
   count_launch();
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {

@@ -92,7 +92,8 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             correct_flags: Optional[torch.Tensor] = None,
             xy_index_map: Optional[torch.Tensor] = None, save_interval: int = 0,
             save_keys=("t", "x", "eps", "P", "y_hat", "S"), want_final: bool = True,
-            skip_predict: bool = False, stream: Optional[torch.cuda.Stream] = None) -> EkfResult:
+            skip_predict: bool = False, dynamic: bool = True,
+            stream: Optional[torch.cuda.Stream] = None) -> EkfResult:
     """Run T EKF steps for a batch of trajectories.
 
     x0 [B, n] (CUDA, float64); P0 [B, n, n] per-trajectory covariance or P0_sqrt [n, n] shared
@@ -151,6 +152,12 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
     io.correct_flags, io.xy_index_map = _dev(flags_k), _dev(map_k)
     io.save_interval = int(save_interval)
     io.skip_predict = int(bool(skip_predict))
+    ws = None
+    if dynamic and save_interval == 0 and not skip_predict and P0_k is None:
+        wsb = int(N.lib().odeu_ekf_workspace_bytes(plan.handle, B, int(T)))
+        if wsb > 0:   # large throughput runs: dynamic (block, time-segment) scheduling
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            io.workspace, io.workspace_bytes = _dev(ws), wsb
 
     xT = epsT = PT = yT = ST = None
     nll = torch.zeros(B, **f64)

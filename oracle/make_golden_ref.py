@@ -172,7 +172,8 @@ def sync_times_fixture():
     print("sync_times fixture:", {k: v.shape for k, v in out.items() if k.endswith("_x")})
 
 
-GRAD_CASES = ["lv_rkf45_temper_q_only", "lv_rkf45_temper_eps_plus_q", "hh_r4_rkf45_temper"]
+GRAD_CASES = ["lv_rkf45_temper_q_only", "lv_rkf45_temper_eps_plus_q", "hh_r4_rkf45_temper",
+              "hh_r1_rkf45_temper", "c3_mhh_r1_rkf45_temper"]
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(cases.CASES)

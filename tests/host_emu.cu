@@ -24,16 +24,31 @@ int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
   constexpr int n = Ode::NX;
   constexpr int KC = LaunchCfg<Ode>::KC;
   const int lk = select_lk<Ode>(io);
-  for (long long b = 0; b < io.B; ++b) {
+  auto run = [&](long long b, const Segment& sg) {
     if constexpr (n <= 4) {
-      if (lk == 0) ekf_trajectory<Ode, Tab, KC, 0>(a, b);
-      else if (lk == 1) ekf_trajectory<Ode, Tab, KC, 1>(a, b);
-      else if (lk == n) ekf_trajectory<Ode, Tab, KC, n>(a, b);
-      else ekf_trajectory<Ode, Tab, KC, -1>(a, b);
+      if (lk == 0) ekf_trajectory<Ode, Tab, KC, 0>(a, b, sg);
+      else if (lk == 1) ekf_trajectory<Ode, Tab, KC, 1>(a, b, sg);
+      else if (lk == n) ekf_trajectory<Ode, Tab, KC, n>(a, b, sg);
+      else ekf_trajectory<Ode, Tab, KC, -1>(a, b, sg);
     } else {
-      ekf_trajectory<Ode, Tab, KC, -1>(a, b);
+      ekf_trajectory<Ode, Tab, KC, -1>(a, b, sg);
     }
+  };
+  if (io.workspace && io.workspace_bytes > 0 && io.save_interval == 0) {
+    // sequential replay of the dynamic scheduler's work items (segment-major), with a
+    // caller-chosen segment length smuggled through workspace_bytes' low bits is NOT needed:
+    // use 7 steps per segment so short test runs cross many boundaries
+    const long long seg_len = 7, nseg = (io.T + seg_len - 1) / seg_len;
+    for (long long seg = 0; seg < nseg; ++seg)
+      for (long long b = 0; b < io.B; ++b) {
+        Segment sg = {seg * seg_len, (seg + 1 == nseg) ? (long long)io.T : (seg + 1) * seg_len, seg == 0,
+                      seg + 1 == nseg, (double*)io.workspace};
+        run(b, sg);
+      }
+    return 0;
   }
+  const Segment whole = {0, (long long)io.T, true, true, nullptr};
+  for (long long b = 0; b < io.B; ++b) run(b, whole);
   return 0;
 }
 template <class Ode, class Tab>

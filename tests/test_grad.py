@@ -15,10 +15,12 @@ from ode_uncertainty_b200 import ode as O
 from ode_uncertainty_b200 import runners
 
 REF_GRAD = {"lv_rkf45_temper_q_only": O.LotkaVolterra, "lv_rkf45_temper_eps_plus_q": O.LotkaVolterra,
-            "hh_r4_rkf45_temper": lambda: O.HodgkinHuxley(model="reduced-4")}
+            "hh_r4_rkf45_temper": lambda: O.HodgkinHuxley(model="reduced-4"),
+            "hh_r1_rkf45_temper": lambda: O.HodgkinHuxley(model="reduced-1"),
+            "c3_mhh_r1_rkf45_temper": lambda: O.MultiCompartmentHodgkinHuxley(model="reduced-1", num_compartments=2)}
 
 
-def _run(backend, name, theta_sorted=None):
+def _run(backend, name, theta_sorted=None, batch=1):
     spec = cases.CASES[name]
     m = cases.materialize(spec)
     plan = cases.make_plan_for(spec)
@@ -29,21 +31,31 @@ def _run(backend, name, theta_sorted=None):
     ths = default_sorted if theta_sorted is None else theta_sorted
     # differentiate every parameter, requested in sorted-key order
     idx_builder = np.array([int(np.nonzero(perm == j)[0][0]) for j in range(perm.size)])
-    nll, g = U.run_grad(backend, plan, m["x0"].reshape(1, -1).numpy(), m["T"], idx_builder, t0=m["t0"],
+    nll, g = U.run_grad(backend, plan, np.repeat(m["x0"].reshape(1, -1).numpy(), batch, 0), m["T"], idx_builder, t0=m["t0"],
                         P0_sqrt=m["P0s"].numpy(), theta_shared=ths[perm], Q_sqrt=m["Q"].numpy(),
                         gamma_sqrt=m["gamma"] ** 0.5, H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(),
                         ys=m["ys"].numpy(), correct_flags=m["flags"], xy_index_map=m["ymap"])
-    return nll[0], g[0], default_sorted
+    return nll[batch - 1], g[batch - 1], default_sorted
 
 
-@pytest.mark.parametrize("name", list(REF_GRAD))
-def test_forward_mode_gradient_matches_reference_reverse_mode(name):
+def _check(backend, name, batch=1):
     ref = dict(np.load(os.path.join(cases.GOLDEN, f"ref_{name}.npz")))
-    nll, g, _ = _run("hostemu", name)
+    nll, g, _ = _run(backend, name, batch=batch)
     assert abs(nll - float(ref["nll_fn"])) <= 1e-9 * abs(float(ref["nll_fn"]))
     g_norm = g * (ref["hi"] - ref["lo"])          # d/d theta_norm = d/d theta * (max - min)
     scale = np.max(np.abs(ref["grad_norm"]))
     np.testing.assert_allclose(g_norm, ref["grad_norm"], rtol=1e-6, atol=1e-6 * scale)
+
+
+@pytest.mark.parametrize("name", list(REF_GRAD))
+def test_forward_mode_gradient_matches_reference_reverse_mode(name):
+    _check("hostemu", name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(REF_GRAD))
+def test_cuda_gradient_matches_reference_reverse_mode(name):
+    _check("gpu", name, batch=37)
 
 
 def test_gradient_matches_finite_differences_lorenz_eps_branch():

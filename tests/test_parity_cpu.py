@@ -110,3 +110,24 @@ def test_invalid_arguments_raise_value_error():
         U.run_ekf("hostemu", plan, np.ones((1, 3)), 5, H=np.ones((4, 3)), R_sqrt=np.eye(4),
                   ys=np.zeros((5, 4)), correct_flags=np.ones(5, np.uint8),
                   xy_index_map=np.arange(5))
+
+
+@pytest.mark.parametrize("name", ["lorenz_rkf45_obs_full", "vdp_rkf45_obs", "lv_rkf45_temper_q_only",
+                                  "c1_lorenz_rkf45_predict"])
+def test_time_segmented_run_is_bitwise_identical(name):
+    """The dynamic scheduler cuts a run into (block, time-segment) items whose state travels
+    through the workspace: replayed sequentially on the host, results equal the one-piece run."""
+    import util as U
+    spec = cases.CASES[name]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    x0 = np.repeat(m["x0"].reshape(1, -1).numpy(), 35, axis=0) + 0.01 * np.arange(35)[:, None]
+    kw = dict(t0=m["t0"], P0_sqrt=m["P0s"].numpy(), Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5)
+    if m["L"] > 0:
+        kw.update(H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy(), correct_flags=m["flags"],
+                  xy_index_map=m["ymap"])
+    whole = U.run_ekf("hostemu", plan, x0, m["T"], **kw)
+    seg = U.run_ekf("hostemu", plan, x0, m["T"], segmented=True, **kw)
+    for k in ("xT", "PT", "nll", "epsT"):
+        np.testing.assert_array_equal(seg[k], whole[k])
+    assert seg["tT"] == whole["tT"]

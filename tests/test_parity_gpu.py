@@ -111,3 +111,29 @@ def test_particle_zero_is_plain_rk_and_ensemble_statistics():
     # sharding invariance: particles [1000, 2000) computed alone equal the same slice of the full run
     part = pf_run(plan, 1000, T, x0_shared=[1., 1., 1.], seed=7, particle_offset=1000, device=dev)
     assert torch.equal(part.xT, r.xT[1000:2000])
+
+
+def test_dynamic_scheduler_equals_static_launch_bitwise():
+    """Persistent (block, time-segment) scheduling vs one static launch at the benchmark batch
+    size: same arithmetic per trajectory, so every output is bit-identical."""
+    from ode_uncertainty_b200 import Plan, ekf_run, _native as N
+    dev = torch.device("cuda:0")
+    for ode_id, n in ((N.ODE_LORENZ, 3), (N.ODE_VAN_DER_POL, 2)):
+        B, T = 65536, 400
+        rng = np.random.default_rng(7)
+        x0 = torch.tensor(1.0 + rng.uniform(-1, 1, (B, n)), device=dev)
+        plan = Plan(ode_id=ode_id, solver_id=N.SOLVER_RKF45, step_size=0.01)
+        assert N.lib().odeu_ekf_workspace_bytes(plan.handle, B, T) > 0
+        ys = torch.tensor(1.0 + 0.1 * rng.normal(size=(T, n)), device=dev)
+        kw = dict(P0_sqrt=np.eye(n), H=np.eye(n), R_sqrt=np.eye(n) * 0.1, ys=ys,
+                  correct_flags=torch.ones(T, dtype=torch.uint8, device=dev),
+                  xy_index_map=torch.arange(T, device=dev))
+        a = ekf_run(plan, x0, T, dynamic=True, **kw)
+        b = ekf_run(plan, x0, T, dynamic=False, **kw)
+        for k in ("xT", "PT", "nll", "epsT", "yhatT", "ST"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+        assert float(a.tT) == float(b.tT)
+        # prediction only as well
+        a = ekf_run(plan, x0, T, dynamic=True)
+        b = ekf_run(plan, x0, T, dynamic=False)
+        assert torch.equal(a.xT, b.xT) and torch.equal(a.PT, b.PT)

@@ -70,8 +70,9 @@ def make_plan(**kw):
 
 def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, theta_shared=None,
             Q_sqrt=None, gamma_sqrt=0.0, H=None, R_sqrt=None, ys=None, ys_per_trajectory=False,
-            correct_flags=None, xy_index_map=None, save_interval=0):
-    """Returns dict(xT [B,n], epsT, PT [B,n,n], nll [B], tT, traj{t,x,eps,P,y_hat,S})."""
+            correct_flags=None, xy_index_map=None, save_interval=0, segmented=False, dynamic=True):
+    """Returns dict(xT [B,n], epsT, PT [B,n,n], nll [B], tT, traj{t,x,eps,P,y_hat,S}).
+    segmented (hostemu): replay the dynamic scheduler's (block, time-segment) items sequentially."""
     x0 = _np(x0)
     B, n = x0.shape
     if backend == "gpu":
@@ -82,7 +83,8 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
                     theta_shared=theta_shared, Q_sqrt=Q_sqrt, gamma_sqrt=gamma_sqrt, H=H,
                     R_sqrt=R_sqrt, ys=tt(ys), ys_per_trajectory=ys_per_trajectory,
                     correct_flags=tt(correct_flags, torch.uint8),
-                    xy_index_map=tt(xy_index_map, torch.int64), save_interval=save_interval)
+                    xy_index_map=tt(xy_index_map, torch.int64), save_interval=save_interval,
+                    dynamic=dynamic)
         torch.cuda.synchronize()
         c = lambda v: None if v is None else v.cpu().numpy()
         out = dict(xT=c(r.xT), epsT=c(r.epsT), PT=c(r.PT), nll=c(r.nll), tT=float(r.tT),
@@ -127,6 +129,9 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
         io.xy_index_map = _p(K(_np(xy_index_map, np.int64)))
     io.L = L
     io.save_interval = int(save_interval)
+    if segmented:
+        wsbuf = K(np.zeros((n + n * n + 1) * B + (B + 31) // 32 + 8))
+        io.workspace, io.workspace_bytes = _p(wsbuf), wsbuf.nbytes
     xT, epsT, PT = np.zeros((n, B)), np.zeros((n, B)), np.zeros((n * n, B))
     yT, ST = np.zeros((max(L, 1), B)), np.zeros((max(L * L, 1), B))
     nll, tT = np.zeros(B), np.zeros(1)

@@ -1,0 +1,74 @@
+"""BASELINE config 3: Hodgkin-Huxley parameter estimation with process-noise
+tempering - batched EKF loss (+ forward-mode gradient) over B parameter sets.
+
+    python tools/bench_c3.py [B] [T] [--grad]
+2-compartment reduced-1 model (n=14, L=2, p=12 optimised scalars), RKF45 h=0.01,
+disable_cov_update, Q_sqrt = I, gamma = 1e-2, R = 0.1, observation every step.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_cpp as RC  # noqa: E402  (data synthesis only)
+from ode_uncertainty_b200 import Plan, _native as N, ekf_grad_run, ekf_run  # noqa: E402
+from ode_uncertainty_b200 import ode as O  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+want_grad = "--grad" in sys.argv
+dev = torch.device("cuda:0")
+ob = O.MultiCompartmentHodgkinHuxley(model="reduced-1", num_compartments=2)
+plan = Plan(N.ODE_MULTI_HH, N.SOLVER_RKF45, 0.01, ode_variant=1, num_compartments=2, disable_cov_update=True)
+th0 = ob.flat_params(ob.params)
+x0 = ob.build_initial_value(np.array([[-70.0, -70.0]]), ob.params).reshape(-1)
+xs, _ = RC.rk_run("MultiHH/reduced-1/2", "RKF45", 0.01, x0, T, theta=th0)
+rng = np.random.default_rng(621)
+ys = xs[1:][:, [0, 7]] + rng.normal(0, 0.1 ** 0.5, (T, 2))
+# optimised parameters and ranges of configs/params/hodgkinhuxley6_c2_r1.yaml:42-58
+names = list(ob.params)
+off, o = {}, 0
+for k in names:
+    off[k] = o
+    o += ob.params[k].size
+opt = ["g_Na", "g_K", "g_leak", "V_T", "g_M", "g_L"]
+idx = np.concatenate([np.arange(off[k], off[k] + 2) for k in opt])
+rngs = {"g_Na": (0.5, 80.0), "g_K": (1e-4, 15.0), "g_leak": (1e-4, 0.6), "V_T": (-90.0, -40.0),
+        "g_M": (1e-5, 0.6), "g_L": (1e-5, 0.6)}
+rng = np.random.default_rng(7)
+theta = np.repeat(th0[None, :], B, 0)
+for k in opt:
+    lo, hi = rngs[k]
+    # stay near the defaults so every parameter set integrates stably with the explicit solver
+    theta[:, off[k]:off[k] + 2] = np.clip(th0[off[k]:off[k] + 2] * (1 + 0.2 * rng.uniform(-1, 1, (B, 2))), lo, hi) \
+        if k != "V_T" else th0[off[k]:off[k] + 2] + rng.uniform(-3, 3, (B, 2))
+H = np.zeros((2, 14)); H[0, 0] = 1; H[1, 7] = 1
+kw = dict(P0_sqrt=np.eye(14) * 1e-12, theta=torch.from_numpy(theta).to(dev), Q_sqrt=np.eye(14), gamma_sqrt=0.1,
+          H=H, R_sqrt=np.eye(2) * 0.1 ** 0.5, ys=torch.from_numpy(ys).to(dev),
+          correct_flags=torch.ones(T, dtype=torch.uint8, device=dev), xy_index_map=torch.arange(T, device=dev))
+x0b = torch.from_numpy(np.repeat(x0[None, :], B, 0)).to(dev)
+
+
+def timed(fn, reps=2):
+    fn(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    return best, out
+
+
+t, r = timed(lambda: ekf_run(plan, x0b, T, want_final=False, **kw))
+units = B * T
+print(f"C3 nll only : B={B} T={T} {t*1e3:.1f} ms  {units/t/1e6:.2f} M param-set-steps/s  "
+      f"{units/t*40.7e3/1e12:.3f} TFLOP/s alg (40.7k flops/unit)  finite={bool(torch.isfinite(r.nll).all())}")
+if want_grad:
+    t, (nll, g) = timed(lambda: ekf_grad_run(plan, x0b, T, idx, **kw), reps=1)
+    print(f"C3 nll+grad : B={B} T={T} p=12 {t*1e3:.1f} ms  {units/t/1e6:.3f} M param-set-steps/s  "
+          f"{units/t*0.99e6/1e12:.3f} TFLOP/s alg (0.99M flops/unit)  finite={bool(torch.isfinite(g).all())}")
+    print("nll agreement grad-kernel vs filter kernel:", float((nll - r.nll).abs().max() / r.nll.abs().max()))

@@ -1,6 +1,6 @@
 // Host launcher of the forward-mode gradient kernel (ekf_grad.cuh).
 #pragma once
-#include "ekf_grad.cuh"
+#include "ekf_coop.cuh"
 #include "plan.h"
 
 namespace odeu {
@@ -12,16 +12,19 @@ struct GradCfg {
   static constexpr int BLOCK = 64;
 };
 
+// `g` may be null: NLL-only use of the cooperative kernel (p_opt = 0).
 template <class Ode>
-int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g,
+int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io* gp,
                    GradArgs<Ode::NX, Ode::NP>& a) {
+  static const odeu_grad_io none = {0, nullptr, nullptr, nullptr};
+  const odeu_grad_io& g = gp ? *gp : none;
   constexpr int n = Ode::NX;
   constexpr int NP = Ode::NP;
   if (io.B <= 0 || io.T < 0) { set_error("odeu_ekf_grad_run: B must be > 0 and T >= 0"); return -1; }
   if (io.L < 0 || io.L > n) { set_error("odeu_ekf_grad_run: L=%d outside [0, n=%d]", io.L, n); return -1; }
   if (!io.x0 || !io.P0_sqrt) { set_error("odeu_ekf_grad_run: x0 and a shared P0_sqrt are required"); return -1; }
   if (io.P0) { set_error("odeu_ekf_grad_run: per-trajectory P0 is not supported"); return -1; }
-  if (g.p_opt < 1 || g.p_opt > ODEU_MAX_GRAD || !g.idx || !g.grad) {
+  if (gp && (g.p_opt < 1 || g.p_opt > ODEU_MAX_GRAD || !g.idx || !g.grad)) {
     set_error("odeu_ekf_grad_run: need 1..%d parameter indices and a grad buffer", ODEU_MAX_GRAD);
     return -1;
   }
@@ -74,11 +77,50 @@ int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad
   return 0;
 }
 
+// Cooperative column-parallel kernel (ekf_coop.cuh) for the medium-size systems.
+template <class Ode>
+constexpr bool coop_eligible_static() { return Ode::NX > 4 && Ode::NX <= 16; }
+template <class Ode>
+bool coop_eligible(const odeu_ekf_io& io) {
+  return coop_eligible_static<Ode>() && 3 * io.L <= Ode::NX && !io.P0 && io.save_interval == 0 &&
+         !io.skip_predict && !io.epsT && !io.yhatT && !io.ST && !io.tT;
+}
+
+template <class Ode, class Tab, class S, int TB>
+int launch_coop_tb(const GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
+  constexpr int n = Ode::NX;
+  const size_t smem = (size_t)2 * n * n * TB * sizeof(S);
+  auto kern = ekf_coop_kernel<Ode, Tab, S, TB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("coop kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
+  const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
+  kern<<<(unsigned)((units + TB - 1) / TB), n * TB, smem, stream>>>(a, PT);
+  return 0;
+}
+
+template <class Ode, class Tab, class S>
+int launch_coop(const GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
+  if constexpr (coop_eligible_static<Ode>()) {
+    constexpr int n = Ode::NX;
+    if ((size_t)2 * n * n * 32 * sizeof(S) <= 220 * 1024) return launch_coop_tb<Ode, Tab, S, 32>(a, PT, stream);
+    return launch_coop_tb<Ode, Tab, S, 16>(a, PT, stream);
+  } else {
+    return -2;
+  }
+}
+
 template <class Ode, class Tab>
 int launch_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g, cudaStream_t stream) {
   using Cfg = GradCfg<Ode>;
   GradArgs<Ode::NX, Ode::NP> a;
-  if (int rc = fill_grad_args<Ode>(plan, io, g, a)) return rc;
+  if (int rc = fill_grad_args<Ode>(plan, io, &g, a)) return rc;
+  if (coop_eligible<Ode>(io)) {
+    if (int rc = launch_coop<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)) return rc;
+    count_launch();
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("odeu_ekf_grad_run: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+    return 0;
+  }
   const int nchunks = (g.p_opt + Cfg::PC - 1) / Cfg::PC;
   dim3 grid((unsigned)((io.B + Cfg::BLOCK - 1) / Cfg::BLOCK), (unsigned)nchunks);
   ekf_grad_kernel<Ode, Tab, Cfg::KC, Cfg::PC, Cfg::BLOCK><<<grid, Cfg::BLOCK, 0, stream>>>(a);
@@ -86,6 +128,31 @@ int launch_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("odeu_ekf_grad_run: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
   return 0;
+}
+
+// NLL-only run of a medium-size system through the cooperative kernel (called by odeu_ekf_run
+// when only nll / xT / PT are requested); returns -100 when the run is not eligible.
+template <class Ode, class Tab>
+int launch_coop_nll(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream) {
+  if (!coop_eligible<Ode>(io)) return -100;
+  GradArgs<Ode::NX, Ode::NP> a;
+  if (int rc = fill_grad_args<Ode>(plan, io, nullptr, a)) return rc;
+  if (int rc = launch_coop<Ode, Tab, double>(a, io.PT, stream)) return rc;
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("odeu_ekf_run: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
+template <class Ode>
+CoopLaunchFn resolve_coop_solver(int solver) {
+  switch (solver) {
+    case ODEU_SOLVER_RKF45: return &launch_coop_nll<Ode, TabRKF45>;
+    case ODEU_SOLVER_DOPRI65: return &launch_coop_nll<Ode, TabDopri65>;
+    case ODEU_SOLVER_BS32: return &launch_coop_nll<Ode, TabBS32>;
+    case ODEU_SOLVER_HEUN_EULER: return &launch_coop_nll<Ode, TabHeunEuler>;
+    default: return nullptr;
+  }
 }
 
 template <class Ode>

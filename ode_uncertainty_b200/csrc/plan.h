@@ -19,6 +19,7 @@ struct odeu_plan {
   int (*rhs_launch)(const odeu_plan&, long long, double, const double*, const double*, const double*,
                     double*, cudaStream_t);
   int (*grad_launch)(const odeu_plan&, const odeu_ekf_io&, const odeu_grad_io&, cudaStream_t);
+  int (*coop_launch)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);   // null for small systems
 };
 
 namespace odeu {
@@ -31,6 +32,9 @@ using PfLaunchFn = int (*)(const odeu_plan&, const odeu_pf_io&, cudaStream_t);
 using RhsLaunchFn = int (*)(const odeu_plan&, long long, double, const double*, const double*,
                            const double*, double*, cudaStream_t);
 using GradLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, const odeu_grad_io&, cudaStream_t);
+using CoopLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);
+CoopLaunchFn resolve_coop_hh(int model, int solver);
+CoopLaunchFn resolve_coop_multi_hh(int model, int nc, int solver);
 GradLaunchFn resolve_grad_small(int ode_id, int variant, int solver);
 GradLaunchFn resolve_grad_hh(int model, int solver);
 GradLaunchFn resolve_grad_multi_hh(int model, int nc, int solver);

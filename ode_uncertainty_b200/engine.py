@@ -92,7 +92,7 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             correct_flags: Optional[torch.Tensor] = None,
             xy_index_map: Optional[torch.Tensor] = None, save_interval: int = 0,
             save_keys=("t", "x", "eps", "P", "y_hat", "S"), want_final: bool = True,
-            skip_predict: bool = False, dynamic: bool = True,
+            skip_predict: bool = False, dynamic: bool = True, minimal: bool = False,
             stream: Optional[torch.cuda.Stream] = None) -> EkfResult:
     """Run T EKF steps for a batch of trajectories.
 
@@ -159,14 +159,16 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             io.workspace, io.workspace_bytes = _dev(ws), wsb
 
+    # minimal=True requests only nll (+ xT, PT with want_final): lets medium-size systems take
+    # the cooperative column-parallel kernel, which does not produce eps / y_hat / S / t outputs
     xT = epsT = PT = yT = ST = None
     nll = torch.zeros(B, **f64)
-    tT = torch.zeros(1, **f64)
+    tT = None if minimal else torch.zeros(1, **f64)
     if want_final:
         xT = torch.empty(n, B, **f64)
-        epsT = torch.empty(n, B, **f64)
+        epsT = None if minimal else torch.empty(n, B, **f64)
         PT = torch.empty(n * n, B, **f64)
-        if L > 0:
+        if L > 0 and not minimal:
             yT = torch.zeros(L, B, **f64)
             ST = torch.zeros(L * L, B, **f64)
     io.xT, io.epsT, io.PT, io.yhatT, io.ST = _dev(xT), _dev(epsT), _dev(PT), _dev(yT), _dev(ST)
@@ -209,7 +211,8 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
                 traj[k] = v.permute(0, 2, 1)
     return EkfResult(
         xT=None if xT is None else xT.t(), epsT=None if epsT is None else epsT.t(),
-        PT=None if PT is None else PT.t().reshape(B, n, n), nll=nll, tT=tT[0],
+        PT=None if PT is None else PT.t().reshape(B, n, n), nll=nll,
+        tT=None if tT is None else tT[0],
         yhatT=None if yT is None else yT.t(),
         ST=None if ST is None else ST.t().reshape(B, L, L), traj=traj)
 

@@ -250,7 +250,8 @@ def ekf_nll(filter_builder, solver_builder, ode_builder, *, params_norm, params_
                 theta=torch.as_tensor(theta).to(dev), Q_sqrt=_arr(Q_sqrt), gamma_sqrt=float(gamma_sqrt),
                 H=H, R_sqrt=_arr(R_sqrt).reshape(L, L), ys=torch.as_tensor(_arr(ys)).to(dev),
                 correct_flags=torch.as_tensor(_arr(correct_flags, np.uint8)).to(dev),
-                xy_index_map=torch.as_tensor(_arr(xy_index_map, np.int64)).to(dev), want_final=False)
+                xy_index_map=torch.as_tensor(_arr(xy_index_map, np.int64)).to(dev), want_final=False,
+                minimal=True)
     return r.nll
 
 

@@ -131,3 +131,29 @@ def test_time_segmented_run_is_bitwise_identical(name):
     for k in ("xT", "PT", "nll", "epsT"):
         np.testing.assert_array_equal(seg[k], whole[k])
     assert seg["tT"] == whole["tT"]
+
+
+@pytest.mark.parametrize("name", ["hh_r1_rkf45_temper", "hh_full_rkf45_small_h", "c3_mhh_r1_rkf45_temper"])
+def test_cooperative_kernel_source_matches_oracle_and_thread_kernel(name):
+    """Medium-size systems: the column-parallel cooperative kernel (ekf_coop.cuh, taken when only
+    nll / xT / PT are requested) against the oracle's final state and the thread-per-trajectory
+    kernel, on a ragged batch of perturbed initial conditions."""
+    import util as U
+    spec = cases.CASES[name]
+    gold = cases.load_golden(name)
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    B = 6
+    x0 = np.repeat(m["x0"].reshape(1, -1).numpy(), B, axis=0)
+    x0[1:, 0] += 0.3 * np.arange(1, B)
+    kw = dict(t0=m["t0"], P0_sqrt=m["P0s"].numpy(), Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5,
+              H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy(), correct_flags=m["flags"],
+              xy_index_map=m["ymap"])
+    coop = U.run_ekf("hostemu", plan, x0, m["T"], minimal=True, **kw)
+    thr = U.run_ekf("hostemu", plan, x0, m["T"], **kw)
+    np.testing.assert_allclose(coop["nll"], thr["nll"], rtol=1e-11)
+    np.testing.assert_allclose(coop["xT"], thr["xT"], rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(coop["PT"], thr["PT"], rtol=1e-9, atol=1e-12 * np.abs(thr["PT"]).max())
+    assert abs(coop["nll"][0] - float(gold["nll"])) <= 1e-9 * abs(float(gold["nll"]))
+    np.testing.assert_allclose(coop["xT"][0], gold["x"][-1], rtol=1e-10)
+    np.testing.assert_allclose(coop["PT"][0], gold["P"][-1], rtol=1e-9, atol=1e-12 * np.abs(gold["P"][-1]).max())

@@ -137,3 +137,23 @@ def test_dynamic_scheduler_equals_static_launch_bitwise():
         a = ekf_run(plan, x0, T, dynamic=True)
         b = ekf_run(plan, x0, T, dynamic=False)
         assert torch.equal(a.xT, b.xT) and torch.equal(a.PT, b.PT)
+
+
+@pytest.mark.parametrize("name", ["hh_r1_rkf45_temper", "hh_full_rkf45_small_h", "c3_mhh_r1_rkf45_temper"])
+def test_cooperative_kernel_on_gpu(name):
+    spec = cases.CASES[name]
+    gold = cases.load_golden(name)
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    B = 75
+    x0 = np.repeat(m["x0"].reshape(1, -1).numpy(), B, axis=0)
+    x0[1:, 0] += 0.02 * np.arange(1, B)
+    kw = dict(t0=m["t0"], P0_sqrt=m["P0s"].numpy(), Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5,
+              H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy(), correct_flags=m["flags"],
+              xy_index_map=m["ymap"])
+    coop = U.run_ekf("gpu", plan, x0, m["T"], minimal=True, **kw)
+    thr = U.run_ekf("gpu", plan, x0, m["T"], **kw)
+    np.testing.assert_allclose(coop["nll"], thr["nll"], rtol=1e-11)
+    np.testing.assert_allclose(coop["xT"], thr["xT"], rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(coop["PT"], thr["PT"], rtol=1e-9, atol=1e-12 * np.abs(thr["PT"]).max())
+    assert abs(coop["nll"][0] - float(gold["nll"])) <= 1e-9 * abs(float(gold["nll"]))

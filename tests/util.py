@@ -70,7 +70,8 @@ def make_plan(**kw):
 
 def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, theta_shared=None,
             Q_sqrt=None, gamma_sqrt=0.0, H=None, R_sqrt=None, ys=None, ys_per_trajectory=False,
-            correct_flags=None, xy_index_map=None, save_interval=0, segmented=False, dynamic=True):
+            correct_flags=None, xy_index_map=None, save_interval=0, segmented=False, dynamic=True,
+            minimal=False):
     """Returns dict(xT [B,n], epsT, PT [B,n,n], nll [B], tT, traj{t,x,eps,P,y_hat,S}).
     segmented (hostemu): replay the dynamic scheduler's (block, time-segment) items sequentially."""
     x0 = _np(x0)
@@ -84,11 +85,11 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
                     R_sqrt=R_sqrt, ys=tt(ys), ys_per_trajectory=ys_per_trajectory,
                     correct_flags=tt(correct_flags, torch.uint8),
                     xy_index_map=tt(xy_index_map, torch.int64), save_interval=save_interval,
-                    dynamic=dynamic)
+                    dynamic=dynamic, minimal=minimal)
         torch.cuda.synchronize()
         c = lambda v: None if v is None else v.cpu().numpy()
-        out = dict(xT=c(r.xT), epsT=c(r.epsT), PT=c(r.PT), nll=c(r.nll), tT=float(r.tT),
-                   yhatT=c(r.yhatT), ST=c(r.ST))
+        out = dict(xT=c(r.xT), epsT=c(r.epsT), PT=c(r.PT), nll=c(r.nll),
+                   tT=None if r.tT is None else float(r.tT), yhatT=c(r.yhatT), ST=c(r.ST))
         out["traj"] = None if r.traj is None else {k: c(v) for k, v in r.traj.items()}
         return out
     assert backend == "hostemu"
@@ -135,7 +136,10 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
     xT, epsT, PT = np.zeros((n, B)), np.zeros((n, B)), np.zeros((n * n, B))
     yT, ST = np.zeros((max(L, 1), B)), np.zeros((max(L * L, 1), B))
     nll, tT = np.zeros(B), np.zeros(1)
-    io.xT, io.epsT, io.PT, io.yhatT, io.ST, io.nll, io.tT = map(_p, (xT, epsT, PT, yT, ST, nll, tT))
+    if minimal:      # only nll, xT, PT requested (lets medium systems take the cooperative kernel)
+        io.xT, io.PT, io.nll = map(_p, (xT, PT, nll))
+    else:
+        io.xT, io.epsT, io.PT, io.yhatT, io.ST, io.nll, io.tT = map(_p, (xT, epsT, PT, yT, ST, nll, tT))
     tr = None
     if save_interval > 0:
         Ts = T // save_interval + 1

@@ -63,7 +63,7 @@ def timed(fn, reps=2):
     return best, out
 
 
-t, r = timed(lambda: ekf_run(plan, x0b, T, want_final=False, **kw))
+t, r = timed(lambda: ekf_run(plan, x0b, T, want_final=False, minimal=True, **kw))
 units = B * T
 print(f"C3 nll only : B={B} T={T} {t*1e3:.1f} ms  {units/t/1e6:.2f} M param-set-steps/s  "
       f"{units/t*40.7e3/1e12:.3f} TFLOP/s alg (40.7k flops/unit)  finite={bool(torch.isfinite(r.nll).all())}")

@@ -89,9 +89,9 @@ struct CoopThread {
 
   // phase 1: RK step with tangent column c -> J[:, c]
   ODEU_HD void phase_rk(const Args& a, S* Asm) {
-    S Jc[n][1];
-    rk_step_generic<Ode, Tab, 1, S>(t, a.h, x, th, c, true, xn, eps, Jc);
-    for (int i = 0; i < n; ++i) at2(Asm, i, c, tl) = Jc[i][0];
+    S Jc[n];
+    rk_step_rolled<Ode, Tab::S>(a, t, x, th, c, xn, eps, Jc);
+    for (int i = 0; i < n; ++i) at2(Asm, i, c, tl) = Jc[i];
   }
   // phase 2: M[:, c] = J P[:, c]
   ODEU_HD void phase_m(S* Asm, S* Bsm) {

@@ -98,8 +98,20 @@ int launch_coop_tb(const GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t
   return 0;
 }
 
+template <class Tab, int NXA, int NPA>
+void fill_rt_tableau(GradArgs<NXA, NPA>& a) {
+  a.rt_S = Tab::S;
+  for (int i = 0; i < 8; ++i) {
+    a.rt_c[i] = i < Tab::S ? Tab::c(i) : 0.0;
+    a.rt_b[0][i] = i < Tab::S ? Tab::b(0, i) : 0.0;
+    a.rt_b[1][i] = i < Tab::S ? Tab::b(1, i) : 0.0;
+    for (int j = 0; j < 8; ++j) a.rt_A[i][j] = (i < Tab::S && j < Tab::S) ? Tab::a(i, j) : 0.0;
+  }
+}
+
 template <class Ode, class Tab, class S>
-int launch_coop(const GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
+int launch_coop(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
+  fill_rt_tableau<Tab>(a);
   if constexpr (coop_eligible_static<Ode>()) {
     constexpr int n = Ode::NX;
     if ((size_t)2 * n * n * 32 * sizeof(S) <= 220 * 1024) return launch_coop_tb<Ode, Tab, S, 32>(a, PT, stream);

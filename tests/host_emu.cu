@@ -21,8 +21,9 @@ void count_launch() {}
 // Sequential replay of one launch of ekf_coop_kernel: the CTA's threads are CoopThread objects,
 // each phase is run for every thread before the next one starts (= __syncthreads()).
 template <class Ode, class Tab, class S>
-int emu_coop(const GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
+int emu_coop(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
   constexpr int n = Ode::NX;
+  fill_rt_tableau<Tab>(a);
   constexpr int TB = 4;                       // small CTA: more CTAs, ragged tail exercised
   using Th = CoopThread<Ode, Tab, S, TB>;
   const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);

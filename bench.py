@@ -171,6 +171,54 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def _other_configs(dev, timed):
+    """Bounded samples of BASELINE configs 3 and 4 for the `extras` block."""
+    import torch
+    from oracle import ref_cpp as RC
+    from ode_uncertainty_b200 import Plan, _native as N, ekf_grad_run, ekf_run, pf_run
+    from ode_uncertainty_b200 import ode as O
+    out = {}
+    # C3: 2-compartment reduced-1 HH, n=14, L=2, p=12, B=4096 parameter sets
+    ob = O.MultiCompartmentHodgkinHuxley(model="reduced-1", num_compartments=2)
+    plan = Plan(N.ODE_MULTI_HH, N.SOLVER_RKF45, 0.01, ode_variant=1, num_compartments=2, disable_cov_update=True)
+    B3, T3 = 4096, 1000
+    th0 = ob.flat_params(ob.params)
+    x0 = ob.build_initial_value(np.array([[-70.0, -70.0]]), ob.params).reshape(-1)
+    xs, _ = RC.rk_run("MultiHH/reduced-1/2", "RKF45", 0.01, x0, T3, theta=th0)
+    rng = np.random.default_rng(621)
+    ys = xs[1:][:, [0, 7]] + rng.normal(0, 0.1 ** 0.5, (T3, 2))
+    names, off, o = list(ob.params), {}, 0
+    for k in names:
+        off[k] = o
+        o += ob.params[k].size
+    opt = ["g_Na", "g_K", "g_leak", "V_T", "g_M", "g_L"]
+    idx = np.concatenate([np.arange(off[k], off[k] + 2) for k in opt])
+    rng = np.random.default_rng(7)
+    theta = np.repeat(th0[None, :], B3, 0)
+    for k in opt:
+        sl = slice(off[k], off[k] + 2)
+        theta[:, sl] = th0[sl] + rng.uniform(-3, 3, (B3, 2)) if k == "V_T" else th0[sl] * (1 + 0.2 * rng.uniform(-1, 1, (B3, 2)))
+    H = np.zeros((2, 14)); H[0, 0] = 1; H[1, 7] = 1
+    kw = dict(P0_sqrt=np.eye(14) * 1e-12, theta=torch.from_numpy(theta).to(dev), Q_sqrt=np.eye(14), gamma_sqrt=0.1,
+              H=H, R_sqrt=np.eye(2) * 0.1 ** 0.5, ys=torch.from_numpy(ys).to(dev),
+              correct_flags=torch.ones(T3, dtype=torch.uint8, device=dev), xy_index_map=torch.arange(T3, device=dev))
+    x0b = torch.from_numpy(np.repeat(x0[None, :], B3, 0)).to(dev)
+    t_nll = timed(lambda: ekf_run(plan, x0b, T3, want_final=False, minimal=True, **kw), reps=1)
+    out["c3_hh_loss"] = {"param_set_steps_per_s": B3 * T3 / t_nll, "sample": f"B={B3} x T={T3} (config: T=10000), n=14, L=2",
+                         "alg_tflops": B3 * T3 / t_nll * 40.7e3 / 1e12}
+    T3g = 200
+    kwg = dict(kw, ys=kw["ys"][:T3g], correct_flags=kw["correct_flags"][:T3g], xy_index_map=kw["xy_index_map"][:T3g])
+    t_g = timed(lambda: ekf_grad_run(plan, x0b, T3g, idx, **kwg), reps=1)
+    out["c3_hh_loss_and_grad"] = {"param_set_steps_per_s": B3 * T3g / t_g, "sample": f"B={B3} x T={T3g}, p=12 forward-mode",
+                                  "alg_tflops": B3 * T3g / t_g * 0.99e6 / 1e12}
+    # C4: particle ensemble (reference-parity part: predict only)
+    planp = Plan(N.ODE_LORENZ, N.SOLVER_RKF45, 0.01)
+    M4, T4 = 1_000_000, 1000
+    t_pf = timed(lambda: pf_run(planp, M4, T4, x0_shared=[1.0, 1.0, 1.0], seed=7, device=dev), reps=1)
+    out["c4_particle_ensemble"] = {"particle_steps_per_s": M4 * T4 / t_pf, "sample": f"M={M4} x T={T4} (config: T=5000) on 1 GPU"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -334,6 +382,13 @@ def main():
                                                       "hbm_write_GBps": bytes_str / t_str / 1e9}
         extras["vdp_traj_steps_per_s"] = B * T / (np.mean(vdp_ms) * 1e-3)
         extras["lorenz_traj_steps_per_s"] = B * T / (np.mean(lorenz_ms) * 1e-3)
+        # other BASELINE configs, bounded samples (not part of `value`): C3 Hodgkin-Huxley
+        # parameter-estimation loss / loss+gradient, C4 particle ensemble
+        if world == 1 and B == 65536 and T == 10000:
+            try:
+                extras.update(_other_configs(dev, timed))
+            except Exception as exc:  # never lose the headline line to an extra
+                extras["other_configs_error"] = f"{type(exc).__name__}: {exc}"
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample
     cpu = None

@@ -137,6 +137,13 @@ int64_t odeu_ekf_workspace_bytes(const odeu_plan* plan, int64_t B, int64_t T);
  * (scripts/run_parameter_estimation.py:771-794).  `cuda_stream` is a cudaStream_t. */
 int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream);
 
+/* EXTENSION (no reference counterpart): bootstrap-weight update for the particle
+ * ensemble, logw_m += log N(y; H x_m, R).  x DEVICE [n][M]; y HOST [L]; H HOST [L][n]; R HOST
+ * [L][L] (full covariance); logw DEVICE [M] in/out.  n, L <= 16. */
+int odeu_pf_weight_update(int64_t M, int32_t n, int32_t L, const double* x_dev, const double* y_host,
+                          const double* H_host, const double* R_host, double* logw_dev,
+                          void* cuda_stream);
+
 /* NLL and its parameter gradient for B parameter sets: replaces jax.value_and_grad(nll) as the
  * optimiser calls it (scripts/run_parameter_estimation.py:599, nll :685-796).  Forward-mode
  * tangents over the requested parameters (at most 32), fused with the filter loop.  Uses from

@@ -21,7 +21,7 @@ SYMBOLS = (
     "odeu_version", "odeu_plan_create", "odeu_plan_destroy", "odeu_plan_state_dim",
     "odeu_plan_num_params", "odeu_plan_default_params", "odeu_ekf_run", "odeu_pf_run",
     "odeu_launch_count", "odeu_last_error", "odeu_bench_dfma", "odeu_ode_rhs",
-    "odeu_ekf_grad_run", "odeu_ekf_workspace_bytes",
+    "odeu_ekf_grad_run", "odeu_ekf_workspace_bytes", "odeu_pf_weight_update",
 )
 
 
@@ -94,6 +94,9 @@ def lib() -> C.CDLL:
     L.odeu_bench_dfma.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                   C.POINTER(C.c_double), C.c_void_p]
     L.odeu_bench_dfma.restype = C.c_int
+    L.odeu_pf_weight_update.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.odeu_pf_weight_update.restype = C.c_int
     L.odeu_ekf_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.odeu_ekf_workspace_bytes.restype = C.c_int64
     L.odeu_ekf_grad_run.argtypes = [C.c_void_p, C.POINTER(EkfIO), C.POINTER(GradIO), C.c_void_p]

@@ -1,0 +1,139 @@
+"""Bootstrap particle filter on top of the perturbed-solver ensemble (EXTENSION).
+
+The reference's `ParticleFilter` only predicts (no weights, no correct step, no resampling;
+src/filters/particle_filter.py:24-118), so there is no reference oracle for this
+module; BASELINE config 4 names its global steps.  Prediction is the reference-parity kernel
+(`odeu_pf_run`); on top of it
+
+    weights      logw += log N(y; H x, R)                 odeu_pf_weight_update (CUDA)
+    normalise    logw -= logsumexp over ALL ranks          all-reduce(max) + all-reduce(sum)
+    ESS          1 / sum w^2                               all-reduce(sum)
+    resample     systematic, when ESS < ess_frac * M:      all-gather of G partial sums, then one
+                 descendants of a rank's particles occupy  all-to-all of the surviving particles
+                 a contiguous range of global slots
+
+Particles are sharded by contiguous global slots (`distributed.shard_bounds`); the random stream
+of the prediction is keyed by global slot and step, the resampling offset by (seed, event), so
+results do not depend on the number of ranks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+from . import distributed as D
+from .engine import Plan, pf_run
+
+
+def weight_update(x: torch.Tensor, logw: torch.Tensor, y, H, R) -> None:
+    """In place: logw_m += log N(y; H x_m, R).  x [M, n] CUDA."""
+    if not x.is_cuda:
+        raise RuntimeError("weight_update runs on the GPU only")
+    M, n = x.shape
+    Hh = np.ascontiguousarray(np.asarray(H, dtype=np.float64))
+    L = Hh.shape[0]
+    yh = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(L))
+    Rh = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(L, L))
+    xk = x.to(torch.float64).t().contiguous()
+    st = torch.cuda.current_stream(x.device)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().odeu_pf_weight_update(M, n, L, C.c_void_p(xk.data_ptr()), yh.ctypes.data_as(C.c_void_p),
+                                              Hh.ctypes.data_as(C.c_void_p), Rh.ctypes.data_as(C.c_void_p),
+                                              C.c_void_p(logw.data_ptr()), C.c_void_p(st.cuda_stream)),
+                "odeu_pf_weight_update")
+
+
+def _count_below(c: torch.Tensor, M_total: int, u0: float) -> torch.Tensor:
+    """Number of systematic positions u_j = (j + u0) / M, j = 0..M-1, with u_j <= c."""
+    k = torch.floor(c * M_total - u0).to(torch.int64) + 1
+    return torch.clamp(k, 0, M_total)
+
+
+def systematic_resample(x: torch.Tensor, logw: torch.Tensor, M_total: int, u0: float) -> torch.Tensor:
+    """Distributed systematic resampling.  x [M_local, n], logw [M_local] globally normalised
+    (sum over all ranks of exp(logw) = 1).  Returns the new local particles [M_local, n] (global
+    slots `shard_bounds(M_total, rank, world)`); weights become uniform."""
+    rank, ws = D.world()
+    w = torch.exp(logw)
+    s_local = w.sum().reshape(1)
+    if ws > 1:
+        sums = [torch.empty_like(s_local) for _ in range(ws)]
+        dist.all_gather(sums, s_local)
+        sums = torch.cat(sums)
+    else:
+        sums = s_local
+    total = sums.sum()
+    c_lo = sums[:rank].sum() / total
+    cdf = c_lo + torch.cumsum(w, 0) / total
+    if rank == ws - 1:
+        cdf[-1] = 1.0                       # the last global particle closes the CDF exactly
+    hi = _count_below(cdf, M_total, u0)
+    lo0 = _count_below(c_lo.reshape(1), M_total, u0)
+    if rank == 0:
+        lo0 = torch.zeros_like(lo0)         # positions u_j <= 0 (u0 = 0) belong to the first particle
+    lo = torch.cat([lo0, hi[:-1]])
+    counts = hi - lo                        # descendants per local particle
+    first_slot = int(lo[0])
+    desc = torch.repeat_interleave(torch.arange(x.shape[0], device=x.device), counts)
+    x_desc = x[desc]                        # ordered by global slot, occupying [first_slot, first_slot + len)
+    if ws == 1:
+        return x_desc
+    n_desc = x_desc.shape[0]
+    send = []
+    for r in range(ws):
+        r_lo, r_hi = D.shard_bounds(M_total, r, ws)
+        a, b = max(first_slot, r_lo), min(first_slot + n_desc, r_hi)
+        send.append(max(0, b - a))
+    send_t = torch.tensor(send, dtype=torch.int64, device=x.device)
+    recv_t = torch.empty_like(send_t)
+    dist.all_to_all_single(recv_t, send_t)
+    recv = recv_t.tolist()
+    out = torch.empty((sum(recv), x.shape[1]), dtype=x.dtype, device=x.device)
+    dist.all_to_all_single(out, x_desc.contiguous(), output_split_sizes=recv, input_split_sizes=send)
+    return out
+
+
+def _u0(seed: int, event: int) -> float:
+    """Resampling offset in [0, 1): deterministic in (seed, event), identical on all ranks."""
+    g = np.random.Generator(np.random.Philox(key=int(seed) & (2 ** 64 - 1), counter=[event, 0, 0, 0]))
+    return float(g.random())
+
+
+def bootstrap_filter(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R, *, x0_shared,
+                     t0: float = 0.0, seed: int = 7, ess_frac: float = 0.5, theta_shared=None,
+                     device="cuda") -> Dict[str, torch.Tensor]:
+    """Bootstrap particle filter: `obs_every` prediction steps between observations `ys[k]`.
+    Returns local particles, normalised log-weights, per-observation ESS and the resample events,
+    plus the log marginal likelihood estimate."""
+    rank, ws = D.world()
+    lo, hi = D.shard_bounds(M_total, rank, ws)
+    M = hi - lo
+    dev = torch.device(device)
+    n = plan.n
+    x = torch.as_tensor(np.asarray(x0_shared, dtype=np.float64).reshape(1, n)).to(dev).repeat(M, 1)
+    logw = torch.full((M,), -math.log(M_total), dtype=torch.float64, device=dev)
+    t = float(t0)
+    n_obs = T // obs_every
+    ess_hist, resampled, loglik = [], [], 0.0
+    for k in range(n_obs):
+        r = pf_run(plan, M, obs_every, x0=x, t0=t, theta_shared=theta_shared, seed=seed,
+                   particle_offset=lo, step_offset=k * obs_every)
+        x, t = r.xT.contiguous(), float(r.tT)
+        weight_update(x, logw, np.asarray(ys)[k], H, R)
+        lse = D.global_logsumexp(logw)          # log sum_i w_i^{k-1} p(y_k | x_i): likelihood increment
+        loglik += float(lse)
+        logw = logw - lse
+        ess = 1.0 / float(D.allreduce_sum(torch.exp(2.0 * logw).sum().reshape(1)))
+        ess_hist.append(ess)
+        if ess < ess_frac * M_total:
+            x = systematic_resample(x, logw, M_total, _u0(seed, k))
+            logw = torch.full((M,), -math.log(M_total), dtype=torch.float64, device=dev)
+            resampled.append(k)
+    return {"x": x, "logw": logw, "ess": torch.tensor(ess_hist), "resampled": resampled,
+            "loglik": loglik, "t": t}

@@ -41,6 +41,10 @@ struct GradArgs {
   // run-time copy of the tableau for the rolled stage loops of the cooperative kernel
   int rt_S;
   double rt_A[8][8], rt_b[2][8], rt_c[8];
+  // stage-tangent schedule of the row-parallel kernel (ekf_rows.cuh): which stage tangents the
+  // propagated solution needs and where each lives (>= 0 shared-memory slot, -1 registers,
+  // -2 last needed stage: accumulated straight into J)
+  int rw_need[8], rw_slot[8], rw_last;
 };
 
 // Same step as rk_step_generic with ROLLED stage loops and the tableau read from the kernel

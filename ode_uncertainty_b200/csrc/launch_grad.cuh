@@ -1,6 +1,7 @@
 // Host launcher of the forward-mode gradient kernel (ekf_grad.cuh).
 #pragma once
-#include "ekf_coop.cuh"
+#include "ekf_rows.cuh"
+#include <cstdlib>
 #include "plan.h"
 
 namespace odeu {
@@ -109,6 +110,45 @@ void fill_rt_tableau(GradArgs<NXA, NPA>& a) {
   }
 }
 
+// Row-parallel kernel (ekf_rows.cuh) for ODE plugins that expose the row interface.
+template <class Ode, class Tab, class S>
+constexpr bool rows_static_ok() {
+  if constexpr (has_rows<Ode>::value) {
+    return Ode::NX > 4 && RowsSmem<Ode, Tab, S, 32 / Ode::ROW_GROUPS>::bytes <= 227 * 1024;
+  } else {
+    return false;
+  }
+}
+template <class Ode, class Tab, class S>
+bool rows_eligible(const odeu_ekf_io& io) {
+  if constexpr (rows_static_ok<Ode, Tab, S>()) {
+    static const bool off = getenv("ODEU_NO_ROWS") != nullptr;   // A/B switch for measurements
+    return !off && io.L <= ROWS_LMAX && !io.P0 && io.save_interval == 0 && !io.skip_predict && !io.epsT &&
+           !io.yhatT && !io.ST && !io.tT;
+  } else {
+    return false;
+  }
+}
+
+template <class Ode, class Tab, class S>
+int launch_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
+  if constexpr (rows_static_ok<Ode, Tab, S>()) {
+    constexpr int TB = 32 / Ode::ROW_GROUPS;
+    using SM = RowsSmem<Ode, Tab, S, TB>;
+    constexpr int MINB = (2 * (SM::bytes + 1024) <= 228 * 1024) ? 2 : 1;
+    fill_rt_tableau<Tab>(a);
+    fill_rows_schedule<Tab>(a);
+    auto kern = ekf_rows_kernel<Ode, Tab, S, TB, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
+    if (e != cudaSuccess) { set_error("row kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
+    const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
+    kern<<<(unsigned)((units + TB - 1) / TB), 32 * Ode::ROW_CLASSES, SM::bytes, stream>>>(a, PT);
+    return 0;
+  } else {
+    return -2;
+  }
+}
+
 template <class Ode, class Tab, class S>
 int launch_coop(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
   fill_rt_tableau<Tab>(a);
@@ -126,8 +166,9 @@ int launch_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io
   using Cfg = GradCfg<Ode>;
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, &g, a)) return rc;
-  if (coop_eligible<Ode>(io)) {
-    if (int rc = launch_coop<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)) return rc;
+  if (rows_eligible<Ode, Tab, GDual<double, 1>>(io) || coop_eligible<Ode>(io)) {
+    if (int rc = rows_eligible<Ode, Tab, GDual<double, 1>>(io) ? launch_rows<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)
+                                        : launch_coop<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)) return rc;
     count_launch();
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("odeu_ekf_grad_run: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
@@ -146,10 +187,11 @@ int launch_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io
 // when only nll / xT / PT are requested); returns -100 when the run is not eligible.
 template <class Ode, class Tab>
 int launch_coop_nll(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream) {
-  if (!coop_eligible<Ode>(io)) return -100;
+  if (!rows_eligible<Ode, Tab, double>(io) && !coop_eligible<Ode>(io)) return -100;
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, nullptr, a)) return rc;
-  if (int rc = launch_coop<Ode, Tab, double>(a, io.PT, stream)) return rc;
+  if (int rc = rows_eligible<Ode, Tab, double>(io) ? launch_rows<Ode, Tab, double>(a, io.PT, stream)
+                                      : launch_coop<Ode, Tab, double>(a, io.PT, stream)) return rc;
   count_launch();
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("odeu_ekf_run: launch failed: %s", cudaGetErrorString(err)); return (int)err; }

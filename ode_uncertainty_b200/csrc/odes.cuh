@@ -13,6 +13,7 @@
 //   rhs<T,PT>(t, x, th, dx)
 #pragma once
 #include "dual.cuh"
+#include "gdual.cuh"
 
 namespace odeu {
 
@@ -148,6 +149,129 @@ ODEU_HD void rhs_single(double t, const T* x, const PT* th, int stride, T* dx) {
   // f_V (reference :53-58): (sum of currents + I_in / A) / C
   dx[0] = (I + I_in(t) / th[P_A * stride]) / th[P_C * stride];
 }
+// ---------------------------------------------------------------------------------------------
+// Row interface (used by the row-parallel kernel, ekf_rows.cuh): ONE equation of the system
+// together with its non-zero partial derivatives.  Every gate equation depends on two states
+// only (the membrane potential and the gate itself), the voltage equation on the states of its
+// own compartment (+ the neighbours' potentials), so the Jacobian of the right-hand side has
+// DIM + 2 (DIM - 1) (+ coupling) entries per compartment instead of DIM^2, and the 2 `exp` of a
+// gate are evaluated once per stage instead of once per tangent column.
+// The rate functions above are reused with a one-lane dual in V; S is the scalar type of the
+// filter (double, or value + parameter direction for the gradient kernel).
+template <class S> struct ParSingle {
+  const S* th; int st;
+  ODEU_HD const S& operator()(int k) const { return th[k * st]; }
+};
+template <class S, int NC> struct ParMulti {   // flat layout of OdeMultiHH (see below)
+  const S* th; int st; int g;
+  ODEU_HD const S& operator()(int k) const {
+    return k == P_C ? th[(NC - 1) * st] : th[(NC + (k - 1) * NC + g) * st];
+  }
+};
+template <class S> ODEU_HD GDual<S, 1> seed1(const S& v) {
+  GDual<S, 1> r; r.v = v; r.d[0] = S(1.0); return r;
+}
+
+// gate q (1 = m, 2 = h, 3 = n, 4 = p, 5 = q, 6 = r, 7 = u): f = d x_q / dt, dV = df/dV, dX = df/dx_q
+template <int MODEL, class S, class PA>
+ODEU_HD void gate_row(int q, const S& V, const S& xq, const PA& par, S& f, S& dV, S& dX) {
+  using D1 = GDual<S, 1>;
+  D1 al, be;
+  bool rate_form = true;
+  switch (q) {
+    case 1: { const D1 u = seed1<S>(V - par(P_VT)); al = a_m(u); be = b_m(u); break; }
+    case 2: { const D1 u = seed1<S>(V - par(P_VT)); al = a_h(u); be = b_h(u); break; }
+    case 3: { const D1 u = seed1<S>(V - par(P_VT)); al = a_n(u); be = b_n(u); break; }
+    case 5: { const D1 v = seed1<S>(V); al = a_q(v); be = b_q(v); break; }
+    case 6: { const D1 v = seed1<S>(V); al = a_r(v); be = b_r(v); break; }
+    case 4: {   // dp/dt = (p_inf(V) - p) / tau_p(V)
+      const D1 v = seed1<S>(V);
+      const D1 tau = par(P_taumax) / (3.3 * d_exp((v + 35.0) / 20.0) + d_exp(-(v + 35.0) / 20.0));
+      const D1 fd = (p_inf(v) - xq) / tau;
+      f = fd.v; dV = fd.d[0]; dX = -(1.0 / tau.v);
+      rate_form = false;
+      break;
+    }
+    default: {  // 7: du/dt = (u_inf(V + V_x) - u) / tau_u(V + V_x)   (full model only)
+      const D1 w = seed1<S>(V + par(P_Vx));
+      const D1 tau = (30.8 + (211.4 + d_exp((w + 113.2) / 5.0))) / (3.7 * (1.0 + d_exp((w + 84.0) / 3.2)));
+      const D1 uinf = 1.0 / (1.0 + d_exp((w + 81.0) / 4.0));
+      const D1 fd = (uinf - xq) / tau;
+      f = fd.v; dV = fd.d[0]; dX = -(1.0 / tau.v);
+      rate_form = false;
+      break;
+    }
+  }
+  if (rate_form) {   // dx/dt = alpha (1 - x) - beta x
+    const S om = 1.0 - xq;
+    f = al.v * om - be.v * xq;
+    dV = al.d[0] * om - be.d[0] * xq;
+    dX = -(al.v + be.v);
+  }
+}
+
+// voltage equation of one compartment: xc[k * xst] = state k of the compartment;
+// df[k] = d f_V / d x_k, k < dim<MODEL>
+template <int MODEL, class S, class PA>
+ODEU_HD void v_row(double t, const S* xc, int xst, const PA& par, S& f, S* df) {
+  const S& V = xc[0];
+  const S& m = xc[xst];
+  const S& h = xc[2 * xst];
+  const S& nn = xc[3 * xst];
+  const S& gNa = par(P_gNa);
+  const S& gK = par(P_gK);
+  const S& gl = par(P_gleak);
+  const S dNa = par(P_ENa) - V;
+  const S dK = par(P_EK) - V;
+  const S m2 = m * m;
+  const S t1 = gNa * (m2 * m);
+  const S t2 = t1 * h;
+  S I = t2 * dNa;
+  S dv = -t2;
+  df[1] = (3.0 * (gNa * m2)) * h * dNa;
+  df[2] = t1 * dNa;
+  const S n2 = nn * nn;
+  const S u1 = gK * (n2 * n2);
+  I = I + u1 * dK;
+  dv = dv - u1;
+  df[3] = (4.0 * (gK * (n2 * nn))) * dK;
+  I = I + gl * (par(P_Eleak) - V);
+  dv = dv - gl;
+  if (MODEL != 4) {
+    const S& p = xc[4 * xst];
+    const S& qq = xc[5 * xst];
+    const S& rr = xc[6 * xst];
+    const S& gM = par(P_gM);
+    const S& gL = par(P_gL);
+    const S dCa = par(P_ECa) - V;
+    const S w1 = gM * p;
+    I = I + w1 * dK;
+    dv = dv - w1;
+    df[4] = gM * dK;
+    const S v1 = gL * (qq * qq);
+    const S v2 = v1 * rr;
+    I = I + v2 * dCa;
+    dv = dv - v2;
+    df[5] = (2.0 * (gL * qq)) * rr * dCa;
+    df[6] = v1 * dCa;
+    if (MODEL == 0) {
+      const S& uu = xc[7 * xst];
+      const S& gT = par(P_gT);
+      const GDual<S, 1> w = seed1<S>(V + par(P_Vx));
+      const GDual<S, 1> si = 1.0 / (1.0 + d_exp(-(w + 57.0) / 6.2));
+      const S z1 = gT * (si.v * si.v);
+      const S z2 = z1 * uu;
+      I = I + z2 * dCa;
+      df[7] = z1 * dCa;
+      dv = dv + ((gT * (2.0 * (si.v * si.d[0]))) * uu * dCa - z2);
+    }
+  }
+  const S iC = 1.0 / par(P_C);
+  f = (I + I_in(t) / par(P_A)) * iC;
+  df[0] = dv * iC;
+#pragma unroll
+  for (int k = 1; k < dim<MODEL>::value; ++k) df[k] = df[k] * iC;
+}
 }  // namespace hh
 
 template <int MODEL>
@@ -157,6 +281,19 @@ struct OdeHodgkinHuxley {
   template <class T, class PT>
   ODEU_HD static void rhs(double t, const T* x, const PT* th, T* dx) {
     hh::rhs_single<MODEL>(t, x, th, 1, dx);
+  }
+  // ---- row interface (ekf_rows.cuh): row r = g * ROW_CLASSES + q
+  static constexpr int ROW_CLASSES = NX;
+  static constexpr int ROW_GROUPS = 1;
+  static constexpr int NNZ = NX + 2 * (NX - 1);
+  ODEU_HD static constexpr int row_ndep(int q) { return q == 0 ? NX : 2; }
+  ODEU_HD static constexpr int row_off(int, int q) { return q == 0 ? 0 : NX + 2 * (q - 1); }
+  ODEU_HD static constexpr int row_dep(int, int q, int k) { return q == 0 ? k : (k == 0 ? 0 : q); }
+  template <class S>
+  ODEU_HD static void row(int q, int, double t, const S* xs, int xst, const S* th, int tst, S& f, S* df) {
+    const hh::ParSingle<S> par{th, tst};
+    if (q == 0) hh::v_row<MODEL>(t, xs, xst, par, f, df);
+    else hh::gate_row<MODEL>(q, xs[0], xs[q * xst], par, f, df[0], df[1]);
   }
 };
 
@@ -193,6 +330,47 @@ struct OdeMultiHH {
         acc = any ? acc + r : r;
       }
       dx[c * DIM] = dx[c * DIM] + acc / Cm;
+    }
+  }
+  // ---- row interface (ekf_rows.cuh): row r = g * DIM + q, g = compartment, q = equation.
+  // The voltage row depends on the DIM states of its compartment and on the potentials of the
+  // neighbouring compartments (NBR slots; a chain end points at its own potential with a zero
+  // coefficient, like the zero entries of the reference's dense `G @ V`, :374-383).
+  static constexpr int ROW_CLASSES = DIM;
+  static constexpr int ROW_GROUPS = NC;
+  static constexpr int NBR = NC == 1 ? 0 : (NC == 2 ? 1 : 2);
+  static constexpr int PER = DIM + NBR + 2 * (DIM - 1);
+  static constexpr int NNZ = NC * PER;
+  ODEU_HD static constexpr int row_ndep(int q) { return q == 0 ? DIM + NBR : 2; }
+  ODEU_HD static constexpr int row_off(int g, int q) {
+    return g * PER + (q == 0 ? 0 : DIM + NBR + 2 * (q - 1));
+  }
+  ODEU_HD static constexpr int nbr_comp(int g, int s) {   // s-th neighbour slot of compartment g
+    return NC == 2 ? 1 - g : (s == 0 ? (g > 0 ? g - 1 : g) : (g + 1 < NC ? g + 1 : g));
+  }
+  ODEU_HD static constexpr int row_dep(int g, int q, int k) {
+    return q == 0 ? (k < DIM ? g * DIM + k : nbr_comp(g, k - DIM) * DIM) : (k == 0 ? g * DIM : g * DIM + q);
+  }
+  template <class S>
+  ODEU_HD static void row(int q, int g, double t, const S* xs, int xst, const S* th, int tst, S& f, S* df) {
+    const hh::ParMulti<S, NC> par{th, tst, g};
+    const S* xc = xs + (long long)g * DIM * xst;
+    if (q != 0) {
+      hh::gate_row<MODEL>(q, xc[0], xc[q * xst], par, f, df[0], df[1]);
+      return;
+    }
+    hh::v_row<MODEL>(t, xc, xst, par, f, df);
+    const S iC = 1.0 / par(hh::P_C);
+#pragma unroll
+    for (int s = 0; s < NBR; ++s) {
+      const int nb = nbr_comp(g, s);
+      // coupling coefficient between g and nb (cc[min(g, nb)]); none at a chain end
+      const bool real = nb != g;
+      const S cc = real ? th[(nb < g ? nb : g) * tst] : S(0.0);
+      f = f + cc * (xs[(long long)nb * DIM * xst] - xc[0]) * iC;
+      const S e = cc * iC;
+      df[0] = df[0] - e;
+      df[DIM + s] = e;
     }
   }
 };

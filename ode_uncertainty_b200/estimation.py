@@ -1,0 +1,197 @@
+"""Parameter estimation with process-noise tempering: the caller of the hot path.
+
+Mirror of `optimize()` / `optimize_run()` of scripts/run_parameter_estimation.py:49-308, 540-682:
+for every tempering stage gamma_s (noise schedule; last stage 0, :621-623) each random run
+minimises the EKF negative log-likelihood over the normalised parameters in [0, 1]^p with
+SciPy's L-BFGS-B - the same optimiser the reference reaches through
+jaxopt.ScipyBoundedMinimize (:599).
+
+What changes is where the (loss, gradient) pairs come from: the reference runs one process per
+random run (`p_umap`, :265-272) and differentiates in reverse mode on the CPU; here all runs
+advance in lock step - every optimiser lives in its own host thread, its requests are collected
+by `BatchedObjective`, and ONE `odeu_ekf_grad_run` launch (forward-mode gradient fused with the
+filter) serves all pending runs.  SciPy sees exactly the function it would see alone, so the
+iterates of a run do not depend on the batching.
+
+Differences to the reference: initial parameters come from NumPy's `default_rng(seed)` instead
+of `jax.random.uniform(key(seed))` (:174-201); results are returned as a dict of NumPy arrays
+with the reference's dataset names (:297-306) instead of being written to H5.
+"""
+from __future__ import annotations
+
+import math
+import threading
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .engine import ekf_grad_run
+from .noise_schedules import ExponentialDecaySchedule, NoiseSchedule
+from .runners import _arr, _plan_for, observation_schedule, param_layout
+
+
+class BatchedObjective:
+    """Lock-step evaluation service for R concurrent optimisers.
+
+    `evaluate(r, z)` blocks until every optimiser that is still running has posted its next
+    point, then one batched kernel launch computes all of them."""
+
+    def __init__(self, num_runs: int, batch_fn) -> None:
+        self.R, self.batch_fn = num_runs, batch_fn
+        self.cv = threading.Condition()
+        self.pending: Dict[int, np.ndarray] = {}
+        self.results: Dict[int, Tuple[float, np.ndarray]] = {}
+        self.active = num_runs
+        self.launches = 0
+        self.error: Optional[BaseException] = None
+
+    def _flush_locked(self) -> None:
+        runs = sorted(self.pending)
+        Z = np.stack([self.pending[r] for r in runs])
+        try:
+            f, g = self.batch_fn(np.array(runs), Z)
+            for k, r in enumerate(runs):
+                self.results[r] = (float(f[k]), np.array(g[k], dtype=np.float64))
+        except BaseException as exc:  # propagate to every waiting optimiser
+            self.error = exc
+            for r in runs:
+                self.results[r] = (float("nan"), np.zeros(Z.shape[1]))
+        self.launches += 1
+        self.pending.clear()
+        self.cv.notify_all()
+
+    def evaluate(self, r: int, z: np.ndarray) -> Tuple[float, np.ndarray]:
+        with self.cv:
+            self.pending[r] = np.array(z, dtype=np.float64)
+            if len(self.pending) == self.active:
+                self._flush_locked()
+            while r not in self.results:
+                self.cv.wait()
+            out = self.results.pop(r)
+            if self.error is not None:
+                raise RuntimeError(str(self.error))
+            return out
+
+    def finish(self, r: int) -> None:
+        with self.cv:
+            self.active -= 1
+            if self.active > 0 and len(self.pending) == self.active:
+                self._flush_locked()
+
+
+def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, measurement_matrix,
+             params_range: Dict[str, Tuple[float, float]], gamma_noise_weights,
+             params_optimized: Optional[Dict[str, bool]] = None, P0=None, t0: float = 0.0, tN: float = 80.0,
+             num_tempering_stages: int = 10, final_gamma_zero: bool = True, obs_noise_var: float = 0.1,
+             gamma_noise_schedule: NoiseSchedule = ExponentialDecaySchedule(), lbfgs_maxiter: int = 200,
+             num_random_runs: int = 0, seed: int = 7, device="cuda", verbose: bool = False
+             ) -> Dict[str, np.ndarray]:
+    """scripts/run_parameter_estimation.py:49-308 with the same keyword meaning (observations
+    are passed as arrays `ts_y`, `ys_x` instead of an H5 path)."""
+    from scipy.optimize import minimize
+
+    if measurement_matrix is None:
+        raise ValueError("Measurement matrix is required!")              # :119-120
+    if gamma_noise_weights is None:
+        raise ValueError("Gamma noise weight vector is required!")       # :121-122
+    if params_range is None:
+        raise ValueError("Parameter ranges are required!")               # :123-124
+    dev = torch.device(device)
+    plan = _plan_for(filter_builder, solver_builder, ode_builder)
+    n = plan.n
+    x0_built = ode_builder.build_initial_value(_arr(x0), ode_builder.params).reshape(-1)
+    P0_sqrt = np.eye(n) * 1e-12 if P0 is None else np.linalg.cholesky(_arr(P0))
+    h = solver_builder.h
+    num_steps, flags, ymap = observation_schedule(t0, tN, h, ts_y)
+    H = _arr(measurement_matrix)
+    L = H.shape[0]
+    assert H.shape[1] == n, "Invalid measurement matrix!"
+    ys = np.einsum("ij,tj->ti", H, _arr(ys_x).reshape(-1, n))            # :147
+    w = _arr(gamma_noise_weights)
+    assert w.shape[0] == n, "Invalid gamma noise weight vector!"
+    keys_s, sizes, perm = param_layout(ode_builder)
+    opt = {k: True for k in keys_s} if params_optimized is None else params_optimized
+    assert len(params_range) == len(ode_builder.params), "Invalid parameter ranges!"
+    opt_keys = [k for k in keys_s if opt[k]]
+    lo = np.concatenate([np.full(sizes[k], params_range[k][0]) for k in opt_keys])
+    hi = np.concatenate([np.full(sizes[k], params_range[k][1]) for k in opt_keys])
+    default_sorted = np.concatenate([np.asarray(ode_builder.params[k], dtype=np.float64).reshape(-1) for k in keys_s])
+    off = np.cumsum([0] + [sizes[k] for k in keys_s])
+    opt_idx_sorted = np.concatenate([np.arange(off[keys_s.index(k)], off[keys_s.index(k) + 1]) for k in opt_keys])
+    inv_perm = np.argsort(perm)                      # builder position of each sorted entry
+    grad_idx_builder = inv_perm[opt_idx_sorted]
+    p = lo.size
+    if num_random_runs > 0:
+        rng = np.random.default_rng(seed)
+        z0 = rng.uniform(0.0, 1.0, (num_random_runs, p))
+        R = num_random_runs
+    else:                                            # single run from the defaults (:203-220)
+        z0 = ((default_sorted[opt_idx_sorted] - lo) / (hi - lo))[None, :]
+        R = 1
+    ys_d = torch.as_tensor(ys).to(dev)
+    flags_d = torch.as_tensor(flags.astype(np.uint8)).to(dev)
+    ymap_d = torch.as_tensor(ymap).to(dev)
+    x0_all = torch.as_tensor(np.repeat(x0_built[None, :], R, axis=0)).to(dev)
+    R_sqrt = np.eye(L) * obs_noise_var ** 0.5
+    Q_sqrt = np.diag(w)
+
+    def batch_fn_factory(gamma):
+        def batch_fn(runs, Z):
+            flat = np.repeat(default_sorted[None, :], len(runs), axis=0)
+            flat[:, opt_idx_sorted] = Z * (hi - lo) + lo                 # inv_normalize (:735-742)
+            theta = torch.as_tensor(flat[:, perm]).to(dev)
+            nll, g = ekf_grad_run(plan, x0_all[: len(runs)], num_steps, grad_idx_builder, t0=t0,
+                                  P0_sqrt=P0_sqrt, theta=theta, Q_sqrt=Q_sqrt, gamma_sqrt=gamma ** 0.5,
+                                  H=H, R_sqrt=R_sqrt, ys=ys_d, correct_flags=flags_d, xy_index_map=ymap_d)
+            return nll.cpu().numpy(), g.cpu().numpy() * (hi - lo)        # d/d theta_norm
+        return batch_fn
+
+    params_optims = np.zeros((R, num_tempering_stages, p))
+    nll_optims = np.zeros((R, num_tempering_stages))
+    iters = np.zeros((R, num_tempering_stages), dtype=np.int64)
+    nfev = np.zeros((R, num_tempering_stages), dtype=np.int64)
+    z = z0.copy()
+    gammas, launches = [], 0
+    for stage in range(num_tempering_stages):
+        gamma = float(gamma_noise_schedule.step(stage))
+        if final_gamma_zero and stage + 1 == num_tempering_stages:
+            gamma = 0.0                                                   # :621-623
+        gammas.append(gamma)
+        svc = BatchedObjective(R, batch_fn_factory(gamma))
+        results = [None] * R
+
+        def worker(r):
+            try:
+                fun = lambda zz, r=r: svc.evaluate(r, zz)
+                results[r] = minimize(fun, z[r], jac=True, method="L-BFGS-B", bounds=[(0.0, 1.0)] * p,
+                                      options={"maxiter": lbfgs_maxiter})
+            except RuntimeError as err:                                   # :657-667: record zeros, go on
+                results[r] = err
+            finally:
+                svc.finish(r)
+
+        threads = [threading.Thread(target=worker, args=(r,)) for r in range(R)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        launches += svc.launches
+        for r in range(R):
+            res = results[r]
+            if isinstance(res, BaseException) or res is None:
+                params_optims[r, stage] = z[r] * (hi - lo) + lo
+                continue
+            z[r] = np.clip(res.x, 0.0, 1.0)
+            params_optims[r, stage] = z[r] * (hi - lo) + lo
+            nll_optims[r, stage] = res.fun
+            iters[r, stage] = res.nit
+            nfev[r, stage] = res.nfev
+        if verbose:
+            print(f"stage {stage + 1}/{num_tempering_stages} gamma={gamma:g} "
+                  f"best nll={nll_optims[:, stage].min():.6g} launches={svc.launches}")
+    names = [k for k in opt_keys for _ in range(sizes[k])]
+    return {"params_inits": z0 * (hi - lo) + lo, "params_optims": params_optims,
+            "params_default": default_sorted[opt_idx_sorted], "params_name": np.array(names),
+            "nll_optims": nll_optims, "num_lbfgs_iters": iters, "num_nll_evals": nfev,
+            "num_nll_jac_evals": nfev.copy(), "gammas": np.array(gammas), "kernel_launches": launches}

@@ -51,8 +51,60 @@ int emu_coop(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
   return 0;
 }
 
+// Sequential replay of one launch of ekf_rows_kernel (same barrier intervals, same order).
+template <class Ode, class Tab, class S>
+int emu_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
+  if constexpr (has_rows<Ode>::value) {
+    constexpr int n = Ode::NX;
+    constexpr int TB = 4;                     // small CTA: ragged tail exercised
+    fill_rt_tableau<Tab>(a);
+    fill_rows_schedule<Tab>(a);
+    using Th = RowThread<Ode, Tab, S, TB>;
+    using SM = RowsSmem<Ode, Tab, S, TB>;
+    const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
+    std::vector<S> sm((size_t)SM::total);
+    std::vector<Th> th((size_t)n * TB);
+    for (long long cta = 0; cta < (units + TB - 1) / TB; ++cta) {
+      for (int k = 0; k < n * TB; ++k) {
+        const int tl = k % TB, g = (k / TB) % Ode::ROW_GROUPS, q = k / (TB * Ode::ROW_GROUPS);
+        th[k].init(a, cta * TB + tl, tl, g, q, sm.data());
+      }
+      for (long long step = 0; step < a.T; ++step) {
+        for (int i = 0; i < a.rt_S; ++i) {
+          for (auto& t : th) t.stage_a(a, i, sm.data());
+          for (auto& t : th) t.stage_b(a, i, sm.data());
+          for (auto& t : th) t.stage_c(a, i, sm.data());
+        }
+        for (auto& t : th) t.phase_x(a, sm.data());
+        for (auto& t : th) t.phase_mp(a, sm.data());
+        for (auto& t : th) t.phase_noise_outer(a, sm.data());
+        if (a.has_obs && a.flags[step]) {
+          const long long oi = a.ymap[step];
+          for (auto& t : th) t.phase_pht(a, sm.data());
+          for (auto& t : th) {
+            double y[ROWS_LMAX];
+            for (int l = 0; l < a.L; ++l) y[l] = a.ys_per_traj ? a.ys[(oi * a.L + l) * a.B + t.b] : a.ys[oi * a.L + l];
+            t.phase_gain(a, y, sm.data());
+          }
+          for (auto& t : th) t.phase_update(a, sm.data());
+        }
+        for (auto& t : th) t.phase_store(sm.data());
+      }
+      for (auto& t : th) t.finish(a, PT, sm.data());
+    }
+    return 0;
+  } else {
+    return -2;
+  }
+}
+
 template <class Ode, class Tab>
 int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
+  if (rows_eligible<Ode, Tab, double>(io) && (plan.desc.ode_id != ODEU_ODE_HODGKIN_HUXLEY || plan.desc.ode_variant != 4)) {
+    GradArgs<Ode::NX, Ode::NP> g;                 // same routing as odeu_ekf_run
+    if (int rc = fill_grad_args<Ode>(plan, io, nullptr, g)) return rc;
+    return emu_rows<Ode, Tab, double>(g, io.PT);
+  }
   if constexpr (coop_eligible_static<Ode>()) {
     if (coop_eligible<Ode>(io)) {           // same routing as odeu_ekf_run
       GradArgs<Ode::NX, Ode::NP> g;
@@ -156,6 +208,7 @@ template <class Ode, class Tab>
 int emu_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g) {
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, &g, a)) return rc;
+  if (rows_eligible<Ode, Tab, GDual<double, 1>>(io)) return emu_rows<Ode, Tab, GDual<double, 1>>(a, nullptr);
   if constexpr (coop_eligible_static<Ode>()) {
     if (coop_eligible<Ode>(io)) return emu_coop<Ode, Tab, GDual<double, 1>>(a, nullptr);
   }

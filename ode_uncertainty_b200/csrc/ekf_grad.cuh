@@ -45,6 +45,7 @@ struct GradArgs {
   // propagated solution needs and where each lives (>= 0 shared-memory slot, -1 registers,
   // -2 last needed stage: accumulated straight into J)
   int rw_need[8], rw_slot[8], rw_last;
+  double rw_ha[8][8], rw_hb1[8];   // h a_ij, h b1_j
 };
 
 // Same step as rk_step_generic with ROLLED stage loops and the tableau read from the kernel

@@ -37,7 +37,8 @@ constexpr int ROWS_LMAX = 4;   // largest observation dimension served by this k
 template <class Ode, class = void> struct has_rows : std::false_type {};
 template <class Ode> struct has_rows<Ode, std::void_t<decltype(Ode::ROW_CLASSES)>> : std::true_type {};
 
-// Which stage tangents the propagated solution needs, and where they are kept.
+// Which stage tangents the propagated solution needs, and where they are kept
+// (compile-time functions of the tableau).
 template <class Tab>
 __host__ __device__ constexpr bool tan_need(int i) {
   bool need[8] = {false, false, false, false, false, false, false, false};
@@ -47,7 +48,7 @@ __host__ __device__ constexpr bool tan_need(int i) {
       if (Tab::a(k, s) != 0.0 && need[k]) nd = true;
     need[s] = nd;
   }
-  return need[i];
+  return i < Tab::S && need[i];
 }
 template <class Tab>
 __host__ __device__ constexpr int tan_last() {
@@ -70,36 +71,50 @@ struct TanSched {
   static constexpr int NREG = NSTORED >= 2 ? 1 : 0;          // newest stored stage in registers
   static constexpr int NSLOT = (NSTORED - NREG) >= 1 ? (NSTORED - NREG) : 1;   // in shared memory
 };
+// >= 0 shared-memory slot, -1 registers, -2 last needed stage (accumulated straight into J),
+// -3 tangent not needed
+template <class Tab>
+__host__ __device__ constexpr int tan_slot(int i) {
+  if (!tan_need<Tab>(i)) return -3;
+  if (i == tan_last<Tab>()) return -2;
+  int stored = 0;
+  for (int k = 0; k <= i; ++k)
+    if (tan_need<Tab>(k)) ++stored;
+  if (TanSched<Tab>::NREG == 1 && stored == TanSched<Tab>::NSTORED) return -1;
+  return stored - 1;
+}
 
+// pre-scaled tableau (constant-bank operands of the tangent DFMAs)
 template <class Tab, int NXA, int NPA>
 void fill_rows_schedule(GradArgs<NXA, NPA>& a) {
-  using TS = TanSched<Tab>;
-  int slot = 0, stored = 0;
-  a.rw_last = TS::LAST;
+  a.rw_last = tan_last<Tab>();
   for (int i = 0; i < 8; ++i) {
-    a.rw_need[i] = (i < Tab::S && tan_need<Tab>(i)) ? 1 : 0;
-    a.rw_slot[i] = -3;
-    if (!a.rw_need[i]) continue;
-    if (i == TS::LAST) { a.rw_slot[i] = -2; continue; }        // accumulated straight into J
-    ++stored;
-    if (TS::NREG == 1 && stored == TS::NSTORED) a.rw_slot[i] = -1;   // register stage
-    else a.rw_slot[i] = slot++;
+    a.rw_need[i] = tan_need<Tab>(i) ? 1 : 0;
+    a.rw_slot[i] = tan_slot<Tab>(i);
+    a.rw_hb1[i] = i < Tab::S ? a.h * Tab::b(1, i) : 0.0;
+    for (int j = 0; j < 8; ++j) a.rw_ha[i][j] = (i < Tab::S && j < Tab::S) ? a.h * Tab::a(i, j) : 0.0;
   }
 }
 
+// Shared-memory map (units of S).  DF, P and the stage tangents use a PAIRED layout when S is a
+// plain double: elements 2e, 2e+1 of one trajectory are adjacent, so one LDS.128 fetches two
+// operands ([e/2][TB][2]); otherwise [e][TB].  X, TH and the measurement exchange are [e][TB].
 template <class Ode, class Tab, class S, int TB>
 struct RowsSmem {
   static constexpr int n = Ode::NX;
+  static constexpr int NP2 = n + (n & 1);              // padded leading dimension (even)
   static constexpr int NSLOT = TanSched<Tab>::NSLOT;
   static constexpr int EXN = 3 * n * ROWS_LMAX;
-  static constexpr bool EX_ALIAS = NSLOT >= 2 && n * n >= EXN;
-  static constexpr long long o_th = 0;
-  static constexpr long long o_x = o_th + (long long)Ode::NP * TB;
-  static constexpr long long o_df = o_x + (long long)n * TB;
-  static constexpr long long o_p = o_df + (long long)(Ode::NNZ > n ? Ode::NNZ : n) * TB;
-  static constexpr long long o_ks = o_p + (long long)n * n * TB;
-  static constexpr long long o_ex = EX_ALIAS ? o_ks + (long long)n * n * TB : o_ks + (long long)NSLOT * n * n * TB;
-  static constexpr long long total = EX_ALIAS ? o_ks + (long long)NSLOT * n * n * TB : o_ex + (long long)EXN * TB;
+  static constexpr int MAT = n * NP2;
+  static constexpr bool EX_ALIAS = NSLOT >= 2 && MAT >= EXN;
+  static constexpr int DFN = ((Ode::NNZ > n ? Ode::NNZ : n) + 1) / 2 * 2;
+  static constexpr int o_th = 0;
+  static constexpr int o_x = o_th + (Ode::NP + (Ode::NP & 1)) * TB;
+  static constexpr int o_df = o_x + NP2 * TB;
+  static constexpr int o_p = o_df + DFN * TB;
+  static constexpr int o_ks = o_p + MAT * TB;
+  static constexpr int o_ex = EX_ALIAS ? o_ks + MAT * TB : o_ks + NSLOT * MAT * TB;
+  static constexpr int total = EX_ALIAS ? o_ks + NSLOT * MAT * TB : o_ex + EXN * TB;
   static constexpr size_t bytes = (size_t)total * sizeof(S);
 };
 
@@ -109,38 +124,60 @@ struct RowThread {
   static constexpr int NP = Ode::NP;
   static constexpr int Q = Ode::ROW_CLASSES;
   static constexpr int G = Ode::ROW_GROUPS;
-  static constexpr int ST = 8;
+  static constexpr int ST = Tab::S;
   static constexpr int LM = ROWS_LMAX;
+  static constexpr int PR = sizeof(S) == 8 ? 2 : 1;
   using Args = GradArgs<Ode::NX, Ode::NP>;
   using SM = RowsSmem<Ode, Tab, S, TB>;
+  static constexpr int NP2 = SM::NP2;
+  static constexpr int MAT = SM::MAT;
   static_assert(Q * G == n, "rows = groups x classes");
 
   // ---- per-thread state
   int tl, g, q, r;
+  int per;         // paired-layout offset of element r
   long long b;
   int chunk;
   bool active;
   double t;
   S x, epsr, nll;
+  S fcur;          // k_i of the stage being evaluated (filed into kp[] with a static index)
   S kp[ST];        // own component of the stage derivatives k_j
   S Kreg[n];       // register-resident stage tangent column
-  S W[n];          // scratch: Y / tangent product / row of M / row of P
+  S W[n];          // scratch: Y / row of P
   S ph[LM], Krow[LM], dvec[LM];
 
-  // ---- shared memory views (trajectory index fastest)
-  ODEU_HD S* TH(S* sm) const { return sm + SM::o_th + tl; }
-  ODEU_HD S* X(S* sm) const { return sm + SM::o_x + tl; }
-  ODEU_HD S* DF(S* sm) const { return sm + SM::o_df + tl; }
-  ODEU_HD S& P(S* sm, int i, int j) const { return sm[SM::o_p + ((long long)i * n + j) * TB + tl]; }
-  ODEU_HD S& KS(S* sm, int slot, int i, int j) const {
-    return sm[SM::o_ks + (((long long)slot * n + i) * n + j) * TB + tl];
+  // ---- shared memory addressing
+  ODEU_HD static constexpr int pe(int e) { return (e / PR) * (TB * PR) + (e % PR); }
+  ODEU_HD S* bl(S* sm) const { return sm + tl; }            // plain layout base
+  ODEU_HD S* bp(S* sm) const { return sm + tl * PR; }       // paired layout base
+  ODEU_HD static void ld2(const S* p, S& u, S& v) {         // elements e (even), e + 1
+    if constexpr (PR == 2) {
+      const double2 w = *reinterpret_cast<const double2*>(p);
+      u = w.x; v = w.y;
+    } else {
+      u = p[0]; v = p[TB];
+    }
   }
+  ODEU_HD static void st2(S* p, const S& u, const S& v) {
+    if constexpr (PR == 2) {
+      *reinterpret_cast<double2*>(p) = make_double2(u, v);
+    } else {
+      p[0] = u; p[TB] = v;
+    }
+  }
+  ODEU_HD S* Xp(S* sm) const { return bl(sm) + SM::o_x; }
+  ODEU_HD S* THp(S* sm) const { return bl(sm) + SM::o_th; }
+  ODEU_HD S* DFp(S* sm) const { return bp(sm) + SM::o_df; }
+  ODEU_HD S* Prow(S* sm, int j) const { return bp(sm) + SM::o_p + j * (NP2 * TB); }        // + pe(k)
+  ODEU_HD S* Kcol(S* sm, int slot, int c) const { return bp(sm) + SM::o_ks + (slot * n + c) * (NP2 * TB); }  // + pe(m)
   ODEU_HD S& EX(S* sm, int which, int i, int l) const {
-    return sm[SM::o_ex + (((long long)which * n + i) * LM + l) * TB + tl];
+    return bl(sm)[SM::o_ex + ((which * n + i) * LM + l) * TB];
   }
 
   ODEU_HD void init(const Args& a, long long unit, int tl_, int g_, int q_, S* sm) {
     tl = tl_; g = g_; q = q_; r = g * Q + q;
+    per = (r / PR) * (TB * PR) + (r % PR);
     const long long total = a.B * (a.p_opt > 0 ? a.p_opt : 1);
     active = unit < total;
     b = active ? unit % a.B : 0;
@@ -152,10 +189,10 @@ struct RowThread {
     for (int k = r; k < NP; k += n) {
       S v = S(a.theta ? a.theta[k * a.B + b] : a.theta_shared[k]);
       seed_theta(a, k, v);
-      TH(sm)[k * TB] = v;
+      THp(sm)[k * TB] = v;
     }
     seed_x0(a);
-    for (int k = 0; k < n; ++k) P(sm, r, k) = S(a.P0s[r * n + k]);
+    for (int k = 0; k < NP2; ++k) Prow(sm, r)[pe(k)] = S(k < n ? a.P0s[r * n + k] : 0.0);
     for (int j = 0; j < ST; ++j) kp[j] = S(0.0);
     for (int m = 0; m < n; ++m) Kreg[m] = S(0.0);
   }
@@ -170,87 +207,139 @@ struct RowThread {
     }
   }
 
-  // ---- stage i, interval A: own component of the stage state  x_i = x + h (ks @ A[i])
-  ODEU_HD void stage_a(const Args& a, int i, S* sm) {
-    S xi = x;
-    if (i > 0) {
-      S s = S(0.0);
+  // ---- stage I, interval A: own component of the stage state  x_i = x + h (ks @ A[i])
+  template <int I>
+  ODEU_HD void stage_a(const Args& a, S* sm) {
+    if constexpr (I < ST) {
+      S xi = x;
+      if constexpr (I > 0) {
+        S s = S(0.0);
+        bool first = true;
 #pragma unroll
-      for (int j = 0; j < ST; ++j)
-        if (j < i && a.rt_A[i][j] != 0.0) s = s + kp[j] * a.rt_A[i][j];
-      xi = x + s * a.h;
+        for (int j = 0; j < I; ++j) {
+          if (Tab::a(I, j) != 0.0) {
+            s = first ? kp[j] * a.rt_A[I][j] : s + kp[j] * a.rt_A[I][j];
+            first = false;
+          }
+        }
+        if (!first) xi = x + s * a.h;
+      }
+      Xp(sm)[r * TB] = xi;
     }
-    X(sm)[r * TB] = xi;
   }
-  // ---- interval B: equation r and its partials at the stage state
+  ODEU_HD void stage_a_rt(const Args& a, int i, S* sm) {
+    switch (i) {
+      case 0: stage_a<0>(a, sm); break;
+      case 1: stage_a<1>(a, sm); break;
+      case 2: stage_a<2>(a, sm); break;
+      case 3: stage_a<3>(a, sm); break;
+      case 4: stage_a<4>(a, sm); break;
+      case 5: stage_a<5>(a, sm); break;
+      case 6: stage_a<6>(a, sm); break;
+      default: stage_a<7>(a, sm); break;
+    }
+  }
+  // ---- interval B: equation r and its partials at the stage state (one copy of the code)
   ODEU_HD void stage_b(const Args& a, int i, S* sm) {
     S f, df[Q + 2];
-    Ode::template row<S>(q, g, t + a.h * a.rt_c[i], X(sm), TB, TH(sm), TB, f, df);
-#pragma unroll
-    for (int j = 0; j < ST; ++j)
-      if (j == i) kp[j] = f;
+    Ode::template row<S>(q, g, t + a.h * a.rt_c[i], Xp(sm), TB, THp(sm), TB, f, df);
+    fcur = f;
     if (a.rw_need[i]) {
-      S* d = DF(sm) + (long long)Ode::row_off(g, q) * TB;
+      S* d = DFp(sm) + Ode::row_off(g, q) * TB;     // row offsets are even
       const int nd = Ode::row_ndep(q);
 #pragma unroll
       for (int k = 0; k < Q + 2; ++k)
-        if (k < nd) d[k * TB] = df[k];
+        if (k < nd) d[pe(k)] = df[k];
     }
   }
-  // ---- interval C: tangent column r of stage i;  after the last needed stage: J[:, r]
-  ODEU_HD void stage_c(const Args& a, int i, S* sm) {
-    if (!a.rw_need[i]) return;
-    // Y = e_r + h sum_j a_ij K'_j[:, r]
+  // ---- interval C: tangent column r of stage I;  after the last needed stage: J[:, r]
+  template <int SLOT>
+  ODEU_HD void add_stage(S* sm, double c) {          // W += c K'_slot[:, r]
+    if constexpr (SLOT >= 0) {
+      const S* kc = Kcol(sm, SLOT, r);
 #pragma unroll
-    for (int m = 0; m < n; ++m) W[m] = S(m == r ? 1.0 : 0.0);
-#pragma unroll 1
-    for (int j = 0; j < i; ++j) {
-      const double c = a.h * a.rt_A[i][j];
-      if (c == 0.0 || !a.rw_need[j]) continue;
-      add_stage(a, sm, j, c);
-    }
-    // K'_i[:, r] = Df_i Y   (static sparsity pattern)
-    S acc[n];
-    const S* d = DF(sm);
-#pragma unroll
-    for (int gm = 0; gm < G; ++gm)
-#pragma unroll
-      for (int qm = 0; qm < Q; ++qm) {
-        S s = d[(long long)Ode::row_off(gm, qm) * TB] * W[Ode::row_dep(gm, qm, 0)];
-#pragma unroll
-        for (int k = 1; k < Ode::row_ndep(qm); ++k)
-          s = s + d[(long long)(Ode::row_off(gm, qm) + k) * TB] * W[Ode::row_dep(gm, qm, k)];
-        acc[gm * Q + qm] = s;
+      for (int m = 0; m + 1 < n; m += 2) {
+        S u, v;
+        ld2(kc + pe(m), u, v);
+        W[m] = W[m] + u * c;
+        W[m + 1] = W[m + 1] + v * c;
       }
-    const int slot = a.rw_slot[i];
-    if (slot >= 0) {
-#pragma unroll
-      for (int m = 0; m < n; ++m) KS(sm, slot, m, r) = acc[m];
-    } else if (slot == -1) {
-#pragma unroll
-      for (int m = 0; m < n; ++m) Kreg[m] = acc[m];
-    } else {   // last needed stage: J[:, r] = e_r + h sum_j b1_j K'_j[:, r]  -> shared (slot 0)
-      const double cl = a.h * a.rt_b[1][i];
-#pragma unroll
-      for (int m = 0; m < n; ++m) W[m] = S(m == r ? 1.0 : 0.0) + acc[m] * cl;
-#pragma unroll 1
-      for (int j = 0; j < i; ++j) {
-        const double c = a.h * a.rt_b[1][j];
-        if (c == 0.0 || !a.rw_need[j]) continue;
-        add_stage(a, sm, j, c);
-      }
-#pragma unroll
-      for (int m = 0; m < n; ++m) KS(sm, 0, m, r) = W[m];
-    }
-  }
-  ODEU_HD void add_stage(const Args& a, S* sm, int j, double c) {
-    const int slot = a.rw_slot[j];
-    if (slot >= 0) {
-#pragma unroll
-      for (int m = 0; m < n; ++m) W[m] = W[m] + KS(sm, slot, m, r) * c;
+      if constexpr (n & 1) W[n - 1] = W[n - 1] + kc[pe(n - 1)] * c;
     } else {
 #pragma unroll
       for (int m = 0; m < n; ++m) W[m] = W[m] + Kreg[m] * c;
+    }
+  }
+  template <int I, int J0, bool BROW>
+  ODEU_HD void add_stages(const Args& a, S* sm) {    // j = J0 .. I-1, coefficients h a_Ij or h b1_j
+    if constexpr (J0 < I) {
+      constexpr double cf = BROW ? Tab::b(1, J0) : Tab::a(I, J0);
+      if constexpr (cf != 0.0 && tan_need<Tab>(J0))
+        add_stage<tan_slot<Tab>(J0)>(sm, BROW ? a.rw_hb1[J0] : a.rw_ha[I][J0]);
+      add_stages<I, J0 + 1, BROW>(a, sm);
+    }
+  }
+  template <int I>
+  ODEU_HD void stage_c(const Args& a, S* sm) {
+    if constexpr (I < ST) kp[I] = fcur;
+    if constexpr (I < ST && tan_need<Tab>(I)) {
+      constexpr int SLOT = tan_slot<Tab>(I);
+      // Y = e_r + h sum_j a_Ij K'_j[:, r]
+#pragma unroll
+      for (int m = 0; m < n; ++m) W[m] = S(m == r ? 1.0 : 0.0);
+      add_stages<I, 0, false>(a, sm);
+      // K'_I[:, r] = Df_I Y   (static sparsity pattern, paired loads of the Jacobian entries)
+      S acc[n];
+      const S* d = DFp(sm);
+#pragma unroll
+      for (int gm = 0; gm < G; ++gm)
+#pragma unroll
+        for (int qm = 0; qm < Q; ++qm) {
+          const int off = Ode::row_off(gm, qm);
+          const int nd = Ode::row_ndep(qm);
+          S s = S(0.0);
+#pragma unroll
+          for (int k = 0; k + 1 < nd; k += 2) {
+            S u, v;
+            ld2(d + pe(off + k), u, v);
+            const S term = u * W[Ode::row_dep(gm, qm, k)] + v * W[Ode::row_dep(gm, qm, k + 1)];
+            s = (k == 0) ? term : s + term;
+          }
+          if (nd & 1) {
+            const S term = d[pe(off + nd - 1)] * W[Ode::row_dep(gm, qm, nd - 1)];
+            s = (nd == 1) ? term : s + term;
+          }
+          acc[gm * Q + qm] = s;
+        }
+      if constexpr (SLOT >= 0) {
+        S* kc = Kcol(sm, SLOT, r);
+#pragma unroll
+        for (int m = 0; m + 1 < n; m += 2) st2(kc + pe(m), acc[m], acc[m + 1]);
+        if constexpr (n & 1) kc[pe(n - 1)] = acc[n - 1];
+      } else if constexpr (SLOT == -1) {
+#pragma unroll
+        for (int m = 0; m < n; ++m) Kreg[m] = acc[m];
+      } else {   // last needed stage: J[:, r] = e_r + h sum_j b1_j K'_j[:, r]  -> shared (slot 0)
+#pragma unroll
+        for (int m = 0; m < n; ++m) W[m] = S(m == r ? 1.0 : 0.0) + acc[m] * a.rw_hb1[I];
+        add_stages<I, 0, true>(a, sm);
+        S* kc = Kcol(sm, 0, r);
+#pragma unroll
+        for (int m = 0; m + 1 < n; m += 2) st2(kc + pe(m), W[m], W[m + 1]);
+        if constexpr (n & 1) kc[pe(n - 1)] = W[n - 1];
+      }
+    }
+  }
+  ODEU_HD void stage_c_rt(const Args& a, int i, S* sm) {
+    switch (i) {
+      case 0: stage_c<0>(a, sm); break;
+      case 1: stage_c<1>(a, sm); break;
+      case 2: stage_c<2>(a, sm); break;
+      case 3: stage_c<3>(a, sm); break;
+      case 4: stage_c<4>(a, sm); break;
+      case 5: stage_c<5>(a, sm); break;
+      case 6: stage_c<6>(a, sm); break;
+      default: stage_c<7>(a, sm); break;
     }
   }
   // ---- after the stages: propagated state (row b[1]), embedded error, time
@@ -258,41 +347,56 @@ struct RowThread {
     S s1 = S(0.0), s0 = S(0.0);
 #pragma unroll
     for (int j = 0; j < ST; ++j) {
-      if (j < a.rt_S) {
-        if (a.rt_b[1][j] != 0.0) s1 = s1 + kp[j] * a.rt_b[1][j];
-        if (a.rt_b[0][j] != 0.0) s0 = s0 + kp[j] * a.rt_b[0][j];
-      }
+      if (Tab::b(1, j) != 0.0) s1 = s1 + kp[j] * a.rt_b[1][j];
+      if (Tab::b(0, j) != 0.0) s0 = s0 + kp[j] * a.rt_b[0][j];
     }
     const S x1 = x + s1 * a.h;
     const S x0 = x + s0 * a.h;
     epsr = d_abs(x0 - x1);
     x = x1;
     t = t + a.h;
-    X(sm)[r * TB] = x;
+    Xp(sm)[r * TB] = x;
   }
-  // ---- row r of M = J P, then of P+ = M J^T + Q
+  // ---- row r of M = J P, then of P+ = M J^T + Q        (J(k, j) = Kcol(0, j)[k])
   ODEU_HD void phase_mp(const Args& a, S* sm) {
     S Jr[n];
 #pragma unroll
-    for (int j = 0; j < n; ++j) Jr[j] = KS(sm, 0, r, j);
+    for (int j = 0; j < n; ++j) Jr[j] = Kcol(sm, 0, j)[per];
     S M[n];
 #pragma unroll
-    for (int k = 0; k < n; ++k) M[k] = Jr[0] * P(sm, 0, k);
+    for (int j = 0; j < n; ++j) {
+      const S* pj = Prow(sm, j);
 #pragma unroll
-    for (int j = 1; j < n; ++j)
+      for (int k = 0; k + 1 < n; k += 2) {
+        S u, v;
+        ld2(pj + pe(k), u, v);
+        M[k] = (j == 0) ? Jr[j] * u : M[k] + Jr[j] * u;
+        M[k + 1] = (j == 0) ? Jr[j] * v : M[k + 1] + Jr[j] * v;
+      }
+      if constexpr (n & 1) {
+        const S u = pj[pe(n - 1)];
+        M[n - 1] = (j == 0) ? Jr[j] * u : M[n - 1] + Jr[j] * u;
+      }
+    }
 #pragma unroll
-      for (int k = 0; k < n; ++k) M[k] = M[k] + Jr[j] * P(sm, j, k);
+    for (int j = 0; j < n; ++j) {
+      const S* kj = Kcol(sm, 0, j);
 #pragma unroll
-    for (int k = 0; k < n; ++k) {
-      S s = M[0] * KS(sm, 0, k, 0);
-#pragma unroll
-      for (int j = 1; j < n; ++j) s = s + M[j] * KS(sm, 0, k, j);
-      W[k] = s;
+      for (int k = 0; k + 1 < n; k += 2) {
+        S u, v;
+        ld2(kj + pe(k), u, v);
+        W[k] = (j == 0) ? M[j] * u : W[k] + M[j] * u;
+        W[k + 1] = (j == 0) ? M[j] * v : W[k + 1] + M[j] * v;
+      }
+      if constexpr (n & 1) {
+        const S u = kj[pe(n - 1)];
+        W[n - 1] = (j == 0) ? M[j] * u : W[n - 1] + M[j] * u;
+      }
     }
     // process noise (src/filters/sqrt_ekf.py:96-136), row r
     if (a.noise_mode == NOISE_COVFN) {
       if (a.cov_fn == COV_DIAGONAL) { const S e = epsr * a.cov_scale; add_diag(e * e); }
-      else if (a.cov_fn == COV_OUTER) DF(sm)[r * TB] = epsr * a.cov_scale;   // exchanged, added in phase_noise_outer
+      else if (a.cov_fn == COV_OUTER) DFp(sm)[per] = epsr * a.cov_scale;   // exchanged, added in phase_noise_outer
       else add_diag(S(a.cov_scale * a.cov_scale));
     } else if (a.noise_mode == NOISE_EPS_PLUS_Q) {
 #pragma unroll
@@ -304,21 +408,26 @@ struct RowThread {
     }
   }
   ODEU_HD void add_diag(const S& v) {
+    // unconditional stores: a guarded `if (k == r)` store is turned into a dynamically indexed
+    // access by the compiler and drags the whole row into local memory
 #pragma unroll
-    for (int k = 0; k < n; ++k)
-      if (k == r) W[k] = W[k] + v;
+    for (int k = 0; k < n; ++k) {
+      const S add = (k == r) ? v : S(0.0);
+      W[k] = W[k] + add;
+    }
   }
   // rank-one process noise of OuterCovarianceUpdate (needs every component of eps):
   // Q = (s eps)(s eps)^T, NaN when eps == 0 like the reference's 0/0 (outer.py:57-60)
   ODEU_HD void phase_noise_outer(const Args& a, S* sm) {
     if (!(a.noise_mode == NOISE_COVFN && a.cov_fn == COV_OUTER)) return;
-    const S er = DF(sm)[r * TB];
+    const S* d = DFp(sm);
+    const S er = d[per];
     double ss = 0.0;
 #pragma unroll
-    for (int k = 0; k < n; ++k) { const double e = scalar_ops<S>::val(DF(sm)[k * TB]); ss += e * e; }
+    for (int k = 0; k < n; ++k) { const double e = scalar_ops<S>::val(d[pe(k)]); ss += e * e; }
     const double poison = (ss == 0.0) ? (ss / ss) : 0.0;
 #pragma unroll
-    for (int k = 0; k < n; ++k) W[k] = W[k] + er * DF(sm)[k * TB] + poison;
+    for (int k = 0; k < n; ++k) W[k] = W[k] + er * d[pe(k)] + poison;
   }
   // ---- measurement update, row-wise.  PHt row r is local (row r of the symmetric P).
   ODEU_HD void phase_pht(const Args& a, S* sm) {
@@ -337,16 +446,19 @@ struct RowThread {
   ODEU_HD void phase_gain(const Args& a, const double* y, S* sm) {
     const int L = a.L;
     S Sm[LM][LM], Ls[LM][LM], inv[LM], z[LM];
+    const S* xs = Xp(sm);
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
       if (l < L) {
-        S s = S(0.0);
-        for (int j = 0; j < n; ++j) s = s + X(sm)[j * TB] * a.H[l * n + j];
+        S s = xs[0] * a.H[l * n];
+#pragma unroll
+        for (int j = 1; j < n; ++j) s = s + xs[j * TB] * a.H[l * n + j];
         dvec[l] = y[l] - s;
 #pragma unroll
         for (int m = 0; m < LM; ++m) {
           if (m <= l) {
             S v = S(a.R[l * L + m]);
+#pragma unroll
             for (int i = 0; i < n; ++i) v = v + EX(sm, 0, i, m) * a.H[l * n + i];
             Sm[l][m] = v;
             Sm[m][l] = v;
@@ -417,6 +529,7 @@ struct RowThread {
 #pragma unroll
         for (int m = 0; m < LM; ++m) if (m < L) gg = gg - Krow[m] * Sm[m][l];
         EX(sm, 1, r, l) = Krow[l];
+        ph[l] = gg;                       // from here on ph holds G_r
         EX(sm, 2, r, l) = gg;
       }
     }
@@ -429,14 +542,15 @@ struct RowThread {
       if (l < L) {
         x = x + Krow[l] * dvec[l];
 #pragma unroll
-        for (int k = 0; k < n; ++k) W[k] = W[k] - Krow[l] * EX(sm, 0, k, l) - ph_g(sm, l) * EX(sm, 1, k, l);
+        for (int k = 0; k < n; ++k) W[k] = W[k] - Krow[l] * EX(sm, 0, k, l) - ph[l] * EX(sm, 1, k, l);
       }
     }
   }
-  ODEU_HD S ph_g(S* sm, int l) const { return EX(sm, 2, r, l); }
   ODEU_HD void phase_store(S* sm) {
+    S* pr = Prow(sm, r);
 #pragma unroll
-    for (int k = 0; k < n; ++k) P(sm, r, k) = W[k];
+    for (int k = 0; k + 1 < n; k += 2) st2(pr + pe(k), W[k], W[k + 1]);
+    if constexpr (n & 1) pr[pe(n - 1)] = W[n - 1];
   }
   ODEU_HD void finish(const Args& a, double* PT, S* sm) {
     if (!active) return;
@@ -444,7 +558,7 @@ struct RowThread {
       if (r == 0 && a.nll) a.nll[b] = scalar_ops<S>::val(nll);
       if (a.xT) a.xT[r * a.B + b] = scalar_ops<S>::val(x);
       if (PT)
-        for (int k = 0; k < n; ++k) PT[((long long)r * n + k) * a.B + b] = scalar_ops<S>::val(P(sm, r, k));
+        for (int k = 0; k < n; ++k) PT[((long long)r * n + k) * a.B + b] = scalar_ops<S>::val(Prow(sm, r)[pe(k)]);
     }
     if constexpr (!std::is_same<S, double>::value) {
       if (r == 0 && a.grad && chunk < a.p_opt) a.grad[(long long)chunk * a.B + b] = nll.d[0];
@@ -464,15 +578,14 @@ ekf_rows_kernel(const __grid_constant__ GradArgs<Ode::NX, Ode::NP> a, double* PT
   const int lane = threadIdx.x & 31;
   th.init(a, (long long)blockIdx.x * TB + lane % TB, lane % TB, lane / TB, threadIdx.x >> 5, sm);
   __syncthreads();
-  const int St = a.rt_S;
   for (long long step = 0; step < a.T; ++step) {
 #pragma unroll 1
-    for (int i = 0; i < St; ++i) {
-      th.stage_a(a, i, sm);
+    for (int i = 0; i < Tab::S; ++i) {
+      th.stage_a_rt(a, i, sm);
       __syncthreads();
       th.stage_b(a, i, sm);
       __syncthreads();
-      th.stage_c(a, i, sm);
+      th.stage_c_rt(a, i, sm);
     }
     th.phase_x(a, sm);
     __syncthreads();

@@ -285,9 +285,10 @@ struct OdeHodgkinHuxley {
   // ---- row interface (ekf_rows.cuh): row r = g * ROW_CLASSES + q
   static constexpr int ROW_CLASSES = NX;
   static constexpr int ROW_GROUPS = 1;
-  static constexpr int NNZ = NX + 2 * (NX - 1);
+  static constexpr int VN = NX + (NX & 1);            // voltage-row slots, padded: row offsets stay even
+  static constexpr int NNZ = VN + 2 * (NX - 1);
   ODEU_HD static constexpr int row_ndep(int q) { return q == 0 ? NX : 2; }
-  ODEU_HD static constexpr int row_off(int, int q) { return q == 0 ? 0 : NX + 2 * (q - 1); }
+  ODEU_HD static constexpr int row_off(int, int q) { return q == 0 ? 0 : VN + 2 * (q - 1); }
   ODEU_HD static constexpr int row_dep(int, int q, int k) { return q == 0 ? k : (k == 0 ? 0 : q); }
   template <class S>
   ODEU_HD static void row(int q, int, double t, const S* xs, int xst, const S* th, int tst, S& f, S* df) {
@@ -339,11 +340,12 @@ struct OdeMultiHH {
   static constexpr int ROW_CLASSES = DIM;
   static constexpr int ROW_GROUPS = NC;
   static constexpr int NBR = NC == 1 ? 0 : (NC == 2 ? 1 : 2);
-  static constexpr int PER = DIM + NBR + 2 * (DIM - 1);
+  static constexpr int VN = (DIM + NBR + 1) / 2 * 2;  // voltage-row slots, padded: row offsets stay even
+  static constexpr int PER = VN + 2 * (DIM - 1);
   static constexpr int NNZ = NC * PER;
   ODEU_HD static constexpr int row_ndep(int q) { return q == 0 ? DIM + NBR : 2; }
   ODEU_HD static constexpr int row_off(int g, int q) {
-    return g * PER + (q == 0 ? 0 : DIM + NBR + 2 * (q - 1));
+    return g * PER + (q == 0 ? 0 : VN + 2 * (q - 1));
   }
   ODEU_HD static constexpr int nbr_comp(int g, int s) {   // s-th neighbour slot of compartment g
     return NC == 2 ? 1 - g : (s == 0 ? (g > 0 ? g - 1 : g) : (g + 1 < NC ? g + 1 : g));

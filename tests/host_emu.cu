@@ -71,9 +71,9 @@ int emu_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
       }
       for (long long step = 0; step < a.T; ++step) {
         for (int i = 0; i < a.rt_S; ++i) {
-          for (auto& t : th) t.stage_a(a, i, sm.data());
+          for (auto& t : th) t.stage_a_rt(a, i, sm.data());
           for (auto& t : th) t.stage_b(a, i, sm.data());
-          for (auto& t : th) t.stage_c(a, i, sm.data());
+          for (auto& t : th) t.stage_c_rt(a, i, sm.data());
         }
         for (auto& t : th) t.phase_x(a, sm.data());
         for (auto& t : th) t.phase_mp(a, sm.data());

@@ -162,6 +162,41 @@ typedef struct {
 int odeu_ekf_grad_run(const odeu_plan* plan, const odeu_ekf_io* io, const odeu_grad_io* grad,
                       void* cuda_stream);
 
+/* Large-state EKF (BASELINE config 5): the oscillator chain of src/ode/lcao.py:51-61 generalised to
+ * D oscillators (plan: ode_id = ODEU_ODE_LCAO, ode_variant = D >= 64, n = 2 D a multiple of 128),
+ * where P <- J P J^T + Q is a dense contraction executed with FP64 tensor-core MMAs.  Replaces the
+ * same `unroll()` / `nll()` loop as odeu_ekf_run (scripts/run_filter.py:166-224) for that shape.
+ * Layout differs from odeu_ekf_io: matrices are stored PER TRAJECTORY, row-major.
+ * The measurement matrix must select state components (rows of the identity: every
+ * measurement_matrix the reference ships has this form); R may be any L x L factor. */
+typedef struct {
+  int64_t B, T;
+  double t0;
+  int32_t L;                      /* number of observed components, 0..16 */
+  const double* x0;               /* DEVICE [B][n] */
+  double* x;                      /* DEVICE [B][n] state, updated in place (may alias x0) */
+  double* P;                      /* DEVICE [B][n][n] covariance, in/out (symmetric) */
+  const double* P0_sqrt;          /* HOST [n][n] shared initial factor, or NULL: P already holds P0 */
+  const double* theta_shared;     /* HOST [3] (lin, cubic, coupling) or NULL = reference defaults */
+  const double* Q_sqrt_diag;      /* HOST [n] diagonal of Q_sqrt (tempering), or NULL */
+  double gamma_sqrt;
+  const int32_t* obs_index;       /* HOST [L] observed state components */
+  const double* R_sqrt;           /* HOST [L][L] */
+  const double* ys;               /* DEVICE [T_obs][L] shared or [T_obs][B][L] */
+  int32_t ys_per_trajectory;
+  const uint8_t* correct_flags;   /* DEVICE [T] */
+  const int64_t* xy_index_map;    /* DEVICE [T] */
+  double* eps;                    /* DEVICE [B][n] last embedded error estimate, or NULL */
+  double* nll;                    /* DEVICE [B] negative log-likelihood */
+  double* tT;                     /* HOST final time, or NULL */
+  void* workspace;                /* DEVICE, odeu_ekf_dense_workspace_bytes(plan, B) bytes */
+  int64_t workspace_bytes;
+} odeu_dense_io;
+
+int64_t odeu_ekf_dense_workspace_bytes(const odeu_plan* plan, int64_t B);
+int odeu_ekf_dense_run(const odeu_plan* plan, const odeu_dense_io* io, void* cuda_stream);
+
+
 /* Perturbed-solver particle ensemble (src/filters/particle_filter.py:24-118; Conrad et al.
  * baseline): M independent RK steps, after each step x += p with p ~ N(0, covfn(0, eps_m));
  * the particle with GLOBAL index 0 is noise-free (:104-105).  The reference draws from JAX's

@@ -5,6 +5,6 @@ buffers.  No CPU fallback: the CUDA library must be built (`make`) and inputs mu
 tensors.
 """
 from . import _native
-from .engine import EkfResult, PfResult, Plan, ekf_grad_run, ekf_run, launch_count, pf_run
+from .engine import DenseResult, EkfResult, PfResult, Plan, ekf_dense_run, ekf_grad_run, ekf_run, launch_count, pf_run
 
-__all__ = ["Plan", "ekf_run", "ekf_grad_run", "pf_run", "EkfResult", "PfResult", "launch_count", "_native"]
+__all__ = ["Plan", "ekf_run", "ekf_grad_run", "pf_run", "ekf_dense_run", "DenseResult", "EkfResult", "PfResult", "launch_count", "_native"]

@@ -22,6 +22,7 @@ SYMBOLS = (
     "odeu_plan_num_params", "odeu_plan_default_params", "odeu_ekf_run", "odeu_pf_run",
     "odeu_launch_count", "odeu_last_error", "odeu_bench_dfma", "odeu_ode_rhs",
     "odeu_ekf_grad_run", "odeu_ekf_workspace_bytes", "odeu_pf_weight_update",
+    "odeu_ekf_dense_run", "odeu_ekf_dense_workspace_bytes",
 )
 
 
@@ -52,6 +53,16 @@ class EkfIO(C.Structure):
 
 class GradIO(C.Structure):
     _fields_ = [("p_opt", C.c_int32), ("idx", _dp), ("x0_tangent", _dp), ("grad", _dp)]
+
+
+class DenseIO(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("T", C.c_int64), ("t0", C.c_double), ("L", C.c_int32),
+        ("x0", _dp), ("x", _dp), ("P", _dp), ("P0_sqrt", _dp), ("theta_shared", _dp),
+        ("Q_sqrt_diag", _dp), ("gamma_sqrt", C.c_double), ("obs_index", _dp), ("R_sqrt", _dp),
+        ("ys", _dp), ("ys_per_trajectory", C.c_int32), ("correct_flags", _dp), ("xy_index_map", _dp),
+        ("eps", _dp), ("nll", _dp), ("tT", _dp), ("workspace", _dp), ("workspace_bytes", C.c_int64),
+    ]
 
 
 class PfIO(C.Structure):
@@ -99,6 +110,10 @@ def lib() -> C.CDLL:
     L.odeu_pf_weight_update.restype = C.c_int
     L.odeu_ekf_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.odeu_ekf_workspace_bytes.restype = C.c_int64
+    L.odeu_ekf_dense_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]
+    L.odeu_ekf_dense_workspace_bytes.restype = C.c_int64
+    L.odeu_ekf_dense_run.argtypes = [C.c_void_p, C.POINTER(DenseIO), C.c_void_p]
+    L.odeu_ekf_dense_run.restype = C.c_int
     L.odeu_ekf_grad_run.argtypes = [C.c_void_p, C.POINTER(EkfIO), C.POINTER(GradIO), C.c_void_p]
     L.odeu_ekf_grad_run.restype = C.c_int
     L.odeu_ode_rhs.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,

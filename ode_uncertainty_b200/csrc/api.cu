@@ -98,7 +98,10 @@ int odeu_plan_create(const odeu_plan_desc* desc, odeu_plan** out) {
     case ODEU_ODE_MULTI_HH: fn = resolve_multi_hh(desc->ode_variant, desc->num_compartments, desc->solver_id); break;
     default: break;
   }
-  if (!fn.ekf) {
+  const bool dense = desc->ode_id == ODEU_ODE_LCAO && desc->ode_variant >= 64 &&
+                     (2 * desc->ode_variant) % 128 == 0 && 2 * desc->ode_variant <= 512 &&
+                     desc->solver_id >= ODEU_SOLVER_RKF45 && desc->solver_id <= ODEU_SOLVER_HEUN_EULER;
+  if (!fn.ekf && !dense) {
     set_error("odeu_plan_create: no kernel for ode=%d variant=%d compartments=%d solver=%d",
               desc->ode_id, desc->ode_variant, desc->num_compartments, desc->solver_id);
     delete p;
@@ -136,6 +139,7 @@ int64_t odeu_ekf_workspace_bytes(const odeu_plan* plan, int64_t B, int64_t T) {
 
 int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream) {
   if (!plan || !io) { set_error("odeu_ekf_run: null argument"); return -1; }
+  if (!plan->ekf_launch) { set_error("odeu_ekf_run: this plan is served by odeu_ekf_dense_run"); return -2; }
   if (plan->coop_launch) {   // medium-size systems: column-parallel cooperative kernel when eligible
     const int rc = plan->coop_launch(*plan, *io, (cudaStream_t)cuda_stream);
     if (rc != -100) return rc;
@@ -145,6 +149,7 @@ int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream
 
 int odeu_pf_run(const odeu_plan* plan, const odeu_pf_io* io, void* cuda_stream) {
   if (!plan || !io) { set_error("odeu_pf_run: null argument"); return -1; }
+  if (!plan->pf_launch) { set_error("odeu_pf_run: no ensemble kernel for this plan"); return -2; }
   return plan->pf_launch(*plan, *io, (cudaStream_t)cuda_stream);
 }
 
@@ -158,6 +163,7 @@ int odeu_ekf_grad_run(const odeu_plan* plan, const odeu_ekf_io* io, const odeu_g
 int odeu_ode_rhs(const odeu_plan* plan, int64_t B, double t, const double* x, const double* theta,
                  const double* theta_shared, double* dx, void* cuda_stream) {
   if (!plan) { set_error("odeu_ode_rhs: null plan"); return -1; }
+  if (!plan->rhs_launch) { set_error("odeu_ode_rhs: not available for this plan"); return -2; }
   return plan->rhs_launch(*plan, (long long)B, t, x, theta, theta_shared, dx, (cudaStream_t)cuda_stream);
 }
 

@@ -277,6 +277,87 @@ def ekf_grad_run(plan: Plan, x0: torch.Tensor, T: int, grad_idx, *, t0: float = 
 
 
 @dataclass
+class DenseResult:
+    """Large-state run (odeu_ekf_dense_run): per-trajectory row-major matrices."""
+    xT: torch.Tensor            # [B, n]
+    PT: torch.Tensor            # [B, n, n]
+    epsT: torch.Tensor          # [B, n]
+    nll: torch.Tensor           # [B]
+    tT: float
+
+
+def ekf_dense_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=None,
+                  P: Optional[torch.Tensor] = None, theta_shared=None, Q_sqrt=None, gamma_sqrt: float = 0.0,
+                  H=None, R_sqrt=None, ys: Optional[torch.Tensor] = None, ys_per_trajectory: bool = False,
+                  correct_flags: Optional[torch.Tensor] = None, xy_index_map: Optional[torch.Tensor] = None,
+                  workspace: Optional[torch.Tensor] = None, inplace: bool = False) -> DenseResult:
+    """T EKF steps of the large-state oscillator chain (BASELINE config 5) on the DMMA path.
+
+    x0 [B, n] CUDA float64.  The initial covariance is either the shared factor P0_sqrt [n, n]
+    (host; default 1e-12 I like scripts/run_filter.py:74-78) or a per-trajectory P [B, n, n]
+    (CUDA; updated IN PLACE when `inplace`, so a run can be resumed without copies).
+    H [L, n] must select state components (rows of the identity); Q_sqrt must be diagonal."""
+    _require_cuda(x0, "x0")
+    dev = x0.device
+    B, n = x0.shape
+    if n != plan.n:
+        raise ValueError(f"x0 has state dimension {n}, plan expects {plan.n}")
+    x = x0.to(torch.float64).contiguous() if inplace else x0.to(torch.float64).clone().contiguous()
+    P0s_h = None
+    if P is None:
+        P0s_h = _host(P0_sqrt, (n, n)) if P0_sqrt is not None else np.eye(n) * 1e-12
+        Pd = torch.empty((B, n, n), dtype=torch.float64, device=dev)
+    else:
+        _require_cuda(P, "P")
+        Pd = P if (inplace and P.dtype == torch.float64 and P.is_contiguous()) else P.to(torch.float64).clone().contiguous()
+    ths_h = _host(theta_shared, (plan.p,)) if theta_shared is not None else None
+    qd_h = None
+    if Q_sqrt is not None:
+        Q_h = _host(Q_sqrt, (n, n))
+        if np.any(Q_h - np.diag(np.diag(Q_h)) != 0.0):
+            raise ValueError("the large-state path takes a diagonal Q_sqrt")
+        qd_h = np.ascontiguousarray(np.diag(Q_h))
+    L = 0
+    idx_h = R_h = ys_k = flags_k = map_k = None
+    if H is not None and ys is not None:
+        H_h = _host(H)
+        L = H_h.shape[0]
+        if H_h.shape != (L, n):
+            raise ValueError("Invalid measurement matrix!")  # scripts/run_filter.py:109
+        idx = H_h.argmax(axis=1)
+        if not np.array_equal(H_h, np.eye(n)[idx]):
+            raise ValueError("the large-state path takes a measurement matrix that selects state components")
+        idx_h = np.ascontiguousarray(idx.astype(np.int32))
+        R_h = _host(R_sqrt, (L, L))
+        _require_cuda(ys, "ys")
+        ys_k = ys.to(torch.float64).contiguous()          # [T_obs, L] or [T_obs, B, L]
+        flags_k = correct_flags.to(device=dev, dtype=torch.uint8).contiguous()
+        map_k = xy_index_map.to(device=dev, dtype=torch.int64).contiguous()
+        if flags_k.numel() < T or map_k.numel() < T:
+            raise ValueError("correct_flags / xy_index_map shorter than T")
+    need = int(N.lib().odeu_ekf_dense_workspace_bytes(plan.handle, B))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 7) // 8, dtype=torch.float64, device=dev)
+    eps = torch.zeros((B, n), dtype=torch.float64, device=dev)
+    nll = torch.zeros(B, dtype=torch.float64, device=dev)
+    tT = C.c_double(t0)
+    io = N.DenseIO()
+    io.B, io.T, io.t0, io.L = B, int(T), float(t0), L
+    io.x0, io.x, io.P, io.P0_sqrt = _dev(x), _dev(x), _dev(Pd), _hp(P0s_h)
+    io.theta_shared, io.Q_sqrt_diag, io.gamma_sqrt = _hp(ths_h), _hp(qd_h), float(gamma_sqrt)
+    io.obs_index = None if idx_h is None else idx_h.ctypes.data_as(C.c_void_p)
+    io.R_sqrt, io.ys, io.ys_per_trajectory = _hp(R_h), _dev(ys_k), int(bool(ys_per_trajectory))
+    io.correct_flags, io.xy_index_map = _dev(flags_k), _dev(map_k)
+    io.eps, io.nll, io.tT = _dev(eps), _dev(nll), C.cast(C.pointer(tT), C.c_void_p)
+    io.workspace, io.workspace_bytes = _dev(workspace), workspace.numel() * workspace.element_size()
+    stream = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().odeu_ekf_dense_run(plan.handle, C.byref(io), C.c_void_p(stream.cuda_stream)),
+                "odeu_ekf_dense_run")
+    return DenseResult(xT=x, PT=Pd, epsT=eps, nll=nll, tT=float(tT.value))
+
+
+@dataclass
 class PfResult:
     xT: torch.Tensor       # [M, n]
     epsT: torch.Tensor     # [M, n]

@@ -108,11 +108,17 @@ class Pendulum(ODEBuilder):
 
 
 class LCAO(ODEBuilder):
-    """src/ode/lcao.py:9-63 (D = 2 positions + 2 velocities)."""
+    """src/ode/lcao.py:9-63 (D = 2 positions + 2 velocities).  The reference's right-hand side
+    works for any number D of oscillators (the coupling is `flip(x)`, :57-59) and takes D from the
+    shape of the state; here `num_oscillators` selects it (128 = BASELINE config 5, served by
+    `ekf_dense_run`)."""
     ode_id, ode_variant, shape = N.ODE_LCAO, 2, (2, 2)
 
-    def __init__(self, lin_coeff: float = 1.0, cubic_coeff: float = 2.0, coupling_coeff: float = 0.5) -> None:
+    def __init__(self, lin_coeff: float = 1.0, cubic_coeff: float = 2.0, coupling_coeff: float = 0.5,
+                 num_oscillators: int = 2) -> None:
         super().__init__(lin_coeff=lin_coeff, cubic_coeff=cubic_coeff, coupling_coeff=coupling_coeff)
+        self.ode_variant = int(num_oscillators)
+        self.shape = (2, int(num_oscillators))
 
 
 # ---- Hodgkin-Huxley steady states for build_initial_value (src/ode/hodgkin_huxley.py:12-36) ----

@@ -57,6 +57,8 @@ def builders(spec):
         ob = ref_ode.MultiCompartmentHodgkinHuxley(model=model, num_compartments=int(nc))
     elif name.startswith("HodgkinHuxley/"):
         ob = ref_ode.HodgkinHuxley(model=name.split("/")[1])
+    elif name.startswith("LCAO/"):
+        ob = ref_ode.LCAO()          # the state shape [2, D] carries D (src/ode/lcao.py:51-61)
     else:
         ob = getattr(ref_ode, name)()
     sb = getattr(ref_solvers, spec["solver"])(step_size=spec.get("h", 0.01))
@@ -175,7 +177,21 @@ def sync_times_fixture():
 GRAD_CASES = ["lv_rkf45_temper_q_only", "lv_rkf45_temper_eps_plus_q", "hh_r4_rkf45_temper",
               "hh_r1_rkf45_temper", "c3_mhh_r1_rkf45_temper"]
 
+def dense_fixture(name):
+    """Large-state cases: the reference code's trajectory, storing the covariance of the last
+    step only (a [T+1, n, n] stack would be megabytes)."""
+    out = run_case(cases.DENSE_CASES[name])
+    keep = dict(t=out["t"], x=out["x"], eps=out["eps"], y_hat=out["y_hat"], nll=out["nll"],
+                P_last=out["P"][-1], P_diag=np.stack([np.diag(p) for p in out["P"]]))
+    np.savez_compressed(os.path.join(cases.GOLDEN, f"ref_{name}.npz"), **keep)
+    print(f"{name}: nll={float(out['nll']):.12g}")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] and sys.argv[1] == "dense":
+        for name in (sys.argv[2:] or list(cases.DENSE_CASES)):
+            dense_fixture(name)
+        sys.exit(0)
     names = sys.argv[1:] or list(cases.CASES)
     if not sys.argv[1:] or "sync_times" in names:
         sync_times_fixture()

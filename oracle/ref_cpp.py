@@ -23,6 +23,14 @@ SOLVER = {"RKF45": 0, "Dopri65": 1, "BS32": 2, "HeunEuler": 3}
 COV = {"diagonal": 0, "outer": 1, "static_diagonal": 2}
 
 
+def ode_key(name: str):
+    """Registry lookup; "LCAO/<D>" = the oscillator chain with D oscillators (n = 2 D)."""
+    if name.startswith("LCAO/"):
+        D = int(name.split("/")[1])
+        return (4, D, 0, 2 * D, 3)
+    return ODE[name]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -53,7 +61,7 @@ def ekf_run(ode: str, solver: str, h: float, x0, T: int, *, t0=0.0, P0_sqrt=None
             save_interval=0, guard="reference", nthreads=0, theta_default=None):
     """x0 [B, n]; theta None (-> theta_default), [p] shared or [B, p].  Returns dict like
     tests/util.run_ekf (xT, PT, nll, traj, guard_mismatch_steps, guard_fired_steps)."""
-    oid, variant, nc, n, p = ODE[ode]
+    oid, variant, nc, n, p = ode_key(ode)
     x0 = _a(x0).reshape(-1, n)
     B = x0.shape[0]
     P0s = _a(np.eye(n) * 1e-12 if P0_sqrt is None else P0_sqrt).reshape(n, n)
@@ -91,7 +99,7 @@ def ekf_run(ode: str, solver: str, h: float, x0, T: int, *, t0=0.0, P0_sqrt=None
 
 
 def rk_run(ode: str, solver: str, h: float, x0, T: int, *, t0=0.0, theta=None):
-    oid, variant, nc, n, p = ODE[ode]
+    oid, variant, nc, n, p = ode_key(ode)
     x0 = _a(x0).reshape(n)
     th = _a(theta)
     xs, es = np.zeros((T + 1, n)), np.zeros((T + 1, n))

@@ -96,7 +96,34 @@ CASES = {
 }
 
 
+def _lcao_x0(D, seed=7):
+    """BASELINE config 5: positions ~ N(0, 1), velocities 0."""
+    rng = np.random.default_rng(seed)
+    return rng.normal(0.0, 1.0, D).tolist() + [0.0] * D
+
+
+# Large-state cases (n = 2 D; served by odeu_ekf_dense_run).  Kept apart from CASES: their
+# fixtures store the covariance of the LAST step only (tests/test_dense.py).
+DENSE_CASES = {
+    # C5 shape at reduced size: first 16 positions observed at every step, P0 = 1e-6 I
+    "c5_lcao64_rkf45_obs": dict(ode="LCAO/64", solver="RKF45", T=12, x0=_lcao_x0(64), P0=1e-6,
+                                obs=(list(range(16)), 1), Rvar=1e-2),
+    # C5 itself (n = 256), few steps
+    "c5_lcao128_rkf45_obs": dict(ode="LCAO/128", solver="RKF45", T=5, x0=_lcao_x0(128), P0=1e-6,
+                                 obs=(list(range(16)), 1), Rvar=1e-2),
+    # tempering branch (diagonal Q), scattered observed components
+    "lcao64_dopri65_temper": dict(ode="LCAO/64", solver="Dopri65", T=8, x0=_lcao_x0(64, 11), P0=1e-4,
+                                  disable=True, Qw=[0.5 + 0.01 * i for i in range(128)], gamma=1e-3,
+                                  obs=([3, 70, 127, 64, 10], 1), Rvar=1e-1, guard="intended"),
+    # prediction only, embedded error as process noise, Heun-Euler (b[1] = [0.5, 0] kept verbatim)
+    "lcao64_bs32_predict": dict(ode="LCAO/64", solver="BS32", T=10, x0=_lcao_x0(64, 3), P0=1e-6, scale=2.0),
+}
+
+
 def ode_and_params(name):
+    if name.startswith("LCAO/"):
+        D = int(name.split("/")[1])
+        return R.ode_lcao, R.ODES["LCAO"][1], (2, D)
     if name.startswith("MultiHH/"):
         _, model, nc = name.split("/")
         return R.make_ode_multi_hh(model, int(nc)), R.multi_hh_default_params(int(nc)), (1, int(nc) * R.HH_DIM[model])
@@ -168,7 +195,10 @@ def load_golden(name):
 
 def make_plan_for(spec):
     from ode_uncertainty_b200 import Plan
-    ode_id, variant, nc = ODE_IDS[spec["ode"]]
+    if spec["ode"].startswith("LCAO/"):
+        ode_id, variant, nc = N.ODE_LCAO, int(spec["ode"].split("/")[1]), 0
+    else:
+        ode_id, variant, nc = ODE_IDS[spec["ode"]]
     return Plan(ode_id=ode_id, solver_id=SOLVERS[spec["solver"]], step_size=spec.get("h", 0.01),
                 ode_variant=variant, num_compartments=nc, cov_fn_id=COVS[spec.get("cov", "diagonal")],
                 cov_scale=spec.get("scale", 1.0), disable_cov_update=spec.get("disable", False))

@@ -216,6 +216,21 @@ def _other_configs(dev, timed):
     M4, T4 = 1_000_000, 1000
     t_pf = timed(lambda: pf_run(planp, M4, T4, x0_shared=[1.0, 1.0, 1.0], seed=7, device=dev), reps=1)
     out["c4_particle_ensemble"] = {"particle_steps_per_s": M4 * T4 / t_pf, "sample": f"M={M4} x T={T4} (config: T=5000) on 1 GPU"}
+    # C5: large-state oscillator chain, n = 256, dense J P J^T on FP64 tensor-core MMAs (DMMA)
+    from ode_uncertainty_b200 import ekf_dense_run
+    D5, n5, L5, B5, T5 = 128, 256, 16, 1024, 20
+    plan5 = Plan(N.ODE_LCAO, N.SOLVER_RKF45, 0.01, ode_variant=D5)
+    rng = np.random.default_rng(7)
+    x05 = torch.from_numpy(np.concatenate([rng.normal(0, 1, (B5, D5)), np.zeros((B5, D5))], axis=1)).to(dev)
+    ys5 = torch.from_numpy(rng.normal(0, 1, (T5, L5))).to(dev)
+    ws5 = torch.empty((int(N.lib().odeu_ekf_dense_workspace_bytes(plan5.handle, B5)) + 7) // 8, dtype=torch.float64, device=dev)
+    kw5 = dict(P0_sqrt=np.eye(n5) * 1e-3, H=np.eye(n5)[:L5], R_sqrt=np.eye(L5) * 0.1, ys=ys5, workspace=ws5,
+               correct_flags=torch.ones(T5, dtype=torch.uint8, device=dev), xy_index_map=torch.arange(T5, device=dev))
+    t5 = timed(lambda: ekf_dense_run(plan5, x05, T5, **kw5), reps=1)
+    out["c5_large_state_dmma"] = {"traj_steps_per_s": B5 * T5 / t5, "ms_per_step": 1e3 * t5 / T5,
+                                  "sample": f"B={B5} x T={T5} (config: T=1000), n=256, L=16",
+                                  "alg_tflops": B5 * T5 / t5 * 77.6e6 / 1e12}
+    del ws5
     return out
 
 
@@ -409,6 +424,14 @@ def main():
             pass
         lor_s = float(np.mean(lorenz_ms)) * 1e-3
         achieved = F_STEP["Lorenz"] * B * T / lor_s / 1e12
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tr.get("B") == B and tr.get("T") == T:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_max / args.steps,
@@ -424,7 +447,7 @@ def main():
                          "frac": achieved / dfma_peak_tflops,
                          "peak_source": "measured in this run: odeu_bench_dfma (8 DFMA chains/thread, 148x8x256 threads)",
                          "algorithmic_flops_per_unit": F_STEP["Lorenz"], "units_per_launch": B * T,
-                         "avg_launch_ms": lor_s * 1e3, "traffic": None,
+                         "avg_launch_ms": lor_s * 1e3, "traffic": traffic,
                          "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -343,20 +343,26 @@ __global__ void __launch_bounds__(512) dense_correct_kernel(const DenseCorrectAr
   }
   a.x[b * n + j] = xn;
   __syncthreads();
-  // P[k][j] -= K_k . PHt_j + G_k . K_j   (column j, coalesced over j; K_k, G_k broadcast)
-  for (int k = 0; k < n; ++k) {
-    double s = Pb[(long long)k * n + j];
-    const double2* kk = reinterpret_cast<const double2*>(Kk + k * DL);
-    const double2* gk = reinterpret_cast<const double2*>(Gk + k * DL);
+  // P[k][j] -= K_k . PHt_j + G_k . K_j   (column j, coalesced over j; K_k, G_k broadcast).
+  // Four rows per iteration and two partial sums per row: eight independent DFMA chains.
+  for (int k = 0; k < n; k += 4) {
+    double pv[4], sa[4], sb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { pv[u] = Pb[(long long)(k + u) * n + j]; sa[u] = 0.0; sb[u] = 0.0; }
 #pragma unroll
     for (int l = 0; l < DL / 2; ++l) {
-      const double2 kv = kk[l], gv = gk[l];
-      s = fma(-kv.x, ph[2 * l], s);
-      s = fma(-kv.y, ph[2 * l + 1], s);
-      s = fma(-gv.x, kj[2 * l], s);
-      s = fma(-gv.y, kj[2 * l + 1], s);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double2 kv = reinterpret_cast<const double2*>(Kk + (k + u) * DL)[l];
+        const double2 gv = reinterpret_cast<const double2*>(Gk + (k + u) * DL)[l];
+        sa[u] = fma(kv.x, ph[2 * l], sa[u]);
+        sb[u] = fma(gv.x, kj[2 * l], sb[u]);
+        sa[u] = fma(kv.y, ph[2 * l + 1], sa[u]);
+        sb[u] = fma(gv.y, kj[2 * l + 1], sb[u]);
+      }
     }
-    Pb[(long long)k * n + j] = s;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Pb[(long long)(k + u) * n + j] = pv[u] - (sa[u] + sb[u]);
   }
 }
 

@@ -118,7 +118,7 @@ struct RowsSmem {
   static constexpr size_t bytes = (size_t)total * sizeof(S);
 };
 
-template <class Ode, class Tab, class S, int TB>
+template <class Ode, class Tab, class S, int TB, int LT = 0>
 struct RowThread {
   static constexpr int n = Ode::NX;
   static constexpr int NP = Ode::NP;
@@ -430,8 +430,10 @@ struct RowThread {
     for (int k = 0; k < n; ++k) W[k] = W[k] + er * d[pe(k)] + poison;
   }
   // ---- measurement update, row-wise.  PHt row r is local (row r of the symmetric P).
+  // LT > 0: observation dimension known at compile time (every predicate below folds away)
+  ODEU_HD static int obs_dim(const Args& a) { return LT > 0 ? LT : a.L; }
   ODEU_HD void phase_pht(const Args& a, S* sm) {
-    const int L = a.L;
+    const int L = obs_dim(a);
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
       if (l < L) {
@@ -444,7 +446,7 @@ struct RowThread {
     }
   }
   ODEU_HD void phase_gain(const Args& a, const double* y, S* sm) {
-    const int L = a.L;
+    const int L = obs_dim(a);
     S Sm[LM][LM], Ls[LM][LM], inv[LM], z[LM];
     const S* xs = Xp(sm);
 #pragma unroll
@@ -536,7 +538,7 @@ struct RowThread {
   }
   // x_r += K_r d;  P+[r, :] = P[r, :] - K_r (H P)[:, :] - G_r K^T
   ODEU_HD void phase_update(const Args& a, S* sm) {
-    const int L = a.L;
+    const int L = obs_dim(a);
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
       if (l < L) {
@@ -568,13 +570,13 @@ struct RowThread {
 
 // One CTA = TB trajectories (or (trajectory, direction) units) x n rows; warp w = row class w,
 // lane = (group, trajectory).  Dynamic shared memory: RowsSmem::bytes.
-template <class Ode, class Tab, class S, int TB, int MINB>
+template <class Ode, class Tab, class S, int TB, int MINB, int LT>
 __global__ void __launch_bounds__(32 * Ode::ROW_CLASSES, MINB)
 ekf_rows_kernel(const __grid_constant__ GradArgs<Ode::NX, Ode::NP> a, double* PT) {
   static_assert(TB * Ode::ROW_GROUPS == 32, "a warp holds every row group of TB trajectories");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S* sm = reinterpret_cast<S*>(smem_raw);
-  RowThread<Ode, Tab, S, TB> th;
+  RowThread<Ode, Tab, S, TB, LT> th;
   const int lane = threadIdx.x & 31;
   th.init(a, (long long)blockIdx.x * TB + lane % TB, lane % TB, lane / TB, threadIdx.x >> 5, sm);
   __syncthreads();
@@ -594,10 +596,11 @@ ekf_rows_kernel(const __grid_constant__ GradArgs<Ode::NX, Ode::NP> a, double* PT
     th.phase_noise_outer(a, sm);
     if (a.has_obs && a.flags[step]) {
       const long long oi = a.ymap[step];
+      const int L = LT > 0 ? LT : a.L;
       double y[ROWS_LMAX];
 #pragma unroll
       for (int l = 0; l < ROWS_LMAX; ++l)
-        if (l < a.L) y[l] = a.ys_per_traj ? a.ys[(oi * a.L + l) * a.B + th.b] : a.ys[oi * a.L + l];
+        if (l < L) y[l] = a.ys_per_traj ? a.ys[(oi * L + l) * a.B + th.b] : a.ys[oi * L + l];
       th.phase_pht(a, sm);
       __syncthreads();
       th.phase_gain(a, y, sm);

@@ -130,20 +130,30 @@ bool rows_eligible(const odeu_ekf_io& io) {
   }
 }
 
+template <class Ode, class Tab, class S, int LT>
+int launch_rows_lt(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
+  constexpr int TB = 32 / Ode::ROW_GROUPS;
+  using SM = RowsSmem<Ode, Tab, S, TB>;
+  constexpr int MINB = (2 * (SM::bytes + 1024) <= 228 * 1024) ? 2 : 1;
+  auto kern = ekf_rows_kernel<Ode, Tab, S, TB, MINB, LT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
+  if (e != cudaSuccess) { set_error("row kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
+  const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
+  kern<<<(unsigned)((units + TB - 1) / TB), 32 * Ode::ROW_CLASSES, SM::bytes, stream>>>(a, PT);
+  return 0;
+}
+
 template <class Ode, class Tab, class S>
 int launch_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
   if constexpr (rows_static_ok<Ode, Tab, S>()) {
-    constexpr int TB = 32 / Ode::ROW_GROUPS;
-    using SM = RowsSmem<Ode, Tab, S, TB>;
-    constexpr int MINB = (2 * (SM::bytes + 1024) <= 228 * 1024) ? 2 : 1;
     fill_rt_tableau<Tab>(a);
     fill_rows_schedule<Tab>(a);
-    auto kern = ekf_rows_kernel<Ode, Tab, S, TB, MINB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
-    if (e != cudaSuccess) { set_error("row kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
-    const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
-    kern<<<(unsigned)((units + TB - 1) / TB), 32 * Ode::ROW_CLASSES, SM::bytes, stream>>>(a, PT);
-    return 0;
+    // the headline tableau gets the observation dimension at compile time (L = number of
+    // compartments / 1: the measurement matrices of configs/params/hodgkinhuxley*.yaml)
+    if constexpr (std::is_same<Tab, TabRKF45>::value) {
+      if (a.L == Ode::ROW_GROUPS && a.has_obs) return launch_rows_lt<Ode, Tab, S, Ode::ROW_GROUPS>(a, PT, stream);
+    }
+    return launch_rows_lt<Ode, Tab, S, 0>(a, PT, stream);
   } else {
     return -2;
   }

@@ -59,7 +59,7 @@ int emu_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
     constexpr int TB = 4;                     // small CTA: ragged tail exercised
     fill_rt_tableau<Tab>(a);
     fill_rows_schedule<Tab>(a);
-    using Th = RowThread<Ode, Tab, S, TB>;
+    using Th = RowThread<Ode, Tab, S, TB, 0>;
     using SM = RowsSmem<Ode, Tab, S, TB>;
     const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
     std::vector<S> sm((size_t)SM::total);

@@ -2,6 +2,11 @@
 tempering - batched EKF loss (+ forward-mode gradient) over B parameter sets.
 
     python tools/bench_c3.py [B] [T] [--grad]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_c3.py [B] [T] [--grad]
+Under torchrun every rank evaluates its own B parameter sets (weak scaling, no data-path
+collective); the batch objective - the sum of the log-likelihoods and of their gradients - is
+formed with ONE NCCL all-reduce of [1 + p] doubles per evaluation, inside the timed
+region; the time reported is the maximum over ranks.
 2-compartment reduced-1 model (n=14, L=2, p=12 optimised scalars), RKF45 h=0.01,
 disable_cov_update, Q_sqrt = I, gamma = 1e-2, R = 0.1, observation every step.
 """
@@ -18,10 +23,20 @@ from oracle import ref_cpp as RC  # noqa: E402  (data synthesis only)
 from ode_uncertainty_b200 import Plan, _native as N, ekf_grad_run, ekf_run  # noqa: E402
 from ode_uncertainty_b200 import ode as O  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+import torch.distributed as dist  # noqa: E402
+from ode_uncertainty_b200 import distributed as D  # noqa: E402
+
+pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+B = int(pos[0]) if len(pos) > 0 else 4096
+T = int(pos[1]) if len(pos) > 1 else 1000
 want_grad = "--grad" in sys.argv
-dev = torch.device("cuda:0")
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
 ob = O.MultiCompartmentHodgkinHuxley(model="reduced-1", num_compartments=2)
 plan = Plan(N.ODE_MULTI_HH, N.SOLVER_RKF45, 0.01, ode_variant=1, num_compartments=2, disable_cov_update=True)
 th0 = ob.flat_params(ob.params)
@@ -39,7 +54,7 @@ opt = ["g_Na", "g_K", "g_leak", "V_T", "g_M", "g_L"]
 idx = np.concatenate([np.arange(off[k], off[k] + 2) for k in opt])
 rngs = {"g_Na": (0.5, 80.0), "g_K": (1e-4, 15.0), "g_leak": (1e-4, 0.6), "V_T": (-90.0, -40.0),
         "g_M": (1e-5, 0.6), "g_L": (1e-5, 0.6)}
-rng = np.random.default_rng(7)
+rng = np.random.default_rng(7 + 1000 * rank)
 theta = np.repeat(th0[None, :], B, 0)
 for k in opt:
     lo, hi = rngs[k]
@@ -57,18 +72,39 @@ def timed(fn, reps=2):
     fn(); torch.cuda.synchronize()
     best = 1e9
     for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1) * 1e-3)
+        tt = D.allreduce_max(torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev))
+        best = min(best, float(tt.item()))
     return best, out
 
 
-t, r = timed(lambda: ekf_run(plan, x0b, T, want_final=False, minimal=True, **kw))
-units = B * T
+def loss_only():
+    res = ekf_run(plan, x0b, T, want_final=False, minimal=True, **kw)
+    res.total = D.allreduce_sum(res.nll.sum().reshape(1))      # batch objective over all ranks
+    return res
+
+
+def loss_and_grad():
+    nll, g = ekf_grad_run(plan, x0b, T, idx, **kw)
+    tot = D.allreduce_sum(torch.cat([nll.sum().reshape(1), g.sum(dim=0)]))   # [1 + p] doubles
+    return nll, g, tot
+
+
+t, r = timed(loss_only)
+units = B * T * world
+if rank != 0:
+    sys.stdout = open(os.devnull, "w")
+print(f"[{world} GPU(s), B={B} parameter sets per GPU]")
 print(f"C3 nll only : B={B} T={T} {t*1e3:.1f} ms  {units/t/1e6:.2f} M param-set-steps/s  "
       f"{units/t*40.7e3/1e12:.3f} TFLOP/s alg (40.7k flops/unit)  finite={bool(torch.isfinite(r.nll).all())}")
 if want_grad:
-    t, (nll, g) = timed(lambda: ekf_grad_run(plan, x0b, T, idx, **kw), reps=1)
+    t, (nll, g, tot) = timed(loss_and_grad, reps=1)
     print(f"C3 nll+grad : B={B} T={T} p=12 {t*1e3:.1f} ms  {units/t/1e6:.3f} M param-set-steps/s  "
           f"{units/t*0.99e6/1e12:.3f} TFLOP/s alg (0.99M flops/unit)  finite={bool(torch.isfinite(g).all())}")
     print("nll agreement grad-kernel vs filter kernel:", float((nll - r.nll).abs().max() / r.nll.abs().max()))
+if world > 1:
+    dist.destroy_process_group()

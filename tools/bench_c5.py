@@ -3,6 +3,8 @@
 observed at every step with R = 1e-2; dense J P J^T on FP64 tensor-core MMAs.
 
     python tools/bench_c5.py [B] [T]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_c5.py [B] [T]
+(weak scaling: B trajectories per GPU, no data-path collective; time = max over ranks).
 Algorithmic flops per trajectory-step: 77.6 M (4 n^3 for the covariance
 propagation + stage tangents + measurement update)."""
 import os
@@ -18,9 +20,16 @@ from ode_uncertainty_b200 import Plan, _native as N, ekf_dense_run  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 D, n, L = 128, 256, 16
-dev = torch.device("cuda:0")
+import torch.distributed as dist  # noqa: E402
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
 plan = Plan(N.ODE_LCAO, N.SOLVER_RKF45, 0.01, ode_variant=D)
-rng = np.random.default_rng(7)
+rng = np.random.default_rng(7 + 1000 * rank)
 x0 = np.concatenate([rng.normal(0, 1, (B, D)), np.zeros((B, D))], axis=1)
 ys = torch.from_numpy(rng.normal(0, 1, (T, L))).to(dev)
 H = np.eye(n)[:L]
@@ -33,8 +42,18 @@ torch.cuda.synchronize()
 best = 1e9
 for _ in range(2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     e0.record(); out = ekf_dense_run(plan, x0d, T, workspace=ws, **kw); e1.record(); torch.cuda.synchronize()
-    best = min(best, e0.elapsed_time(e1) * 1e-3)
-units = B * T
-print(f"C5 dense EKF: B={B} n={n} T={T} L={L}  {best*1e3:.1f} ms  {best/T*1e3:.3f} ms/step  {units/best/1e3:.1f} k trajectory-steps/s  "
+    tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    best = min(best, float(tt.item()))
+units = B * T * world
+if rank != 0:
+    sys.stdout = open(os.devnull, "w")
+print(f"C5 dense EKF [{world} GPU(s)]: B/GPU={B} n={n} T={T} L={L}  {best*1e3:.1f} ms  {best/T*1e3:.3f} ms/step  {units/best/1e3:.1f} k trajectory-steps/s  "
       f"{units/best*77.6e6/1e12:.2f} TFLOP/s alg (77.6 MFLOP/unit)  finite={bool(torch.isfinite(out.nll).all())}")
+if world > 1:
+    dist.destroy_process_group()

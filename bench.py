@@ -240,6 +240,12 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    # stdout carries exactly ONE line (the JSON record): while the bench runs, file descriptor 1
+    # points at stderr so that library banners (NCCL prints its version to stdout) cannot
+    # interleave with it; it is restored just before the record is printed.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -457,7 +463,10 @@ def main():
             "all_finite": finite,
             "extras": extras,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

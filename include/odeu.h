@@ -128,6 +128,12 @@ typedef struct {
   double* out_P;             /* [T_save][n*n][B] */
   double* out_yhat;          /* [T_save][L][B] */
   double* out_S;             /* [T_save][L*L][B] */
+  /* ---- calibration sweep (scripts/run_calibration_conrad_baseline_calibration.py:126-160):
+   * one trajectory per static noise level */
+  const double* cov_scale_batch;  /* DEVICE [B] per-trajectory scale of the covariance-update function
+                                     (overrides the plan's cov_scale), or NULL */
+  int32_t nll_nan_to_num;    /* 1: every per-step term passes through nan_to_num before it is added
+                                (NaN -> 0, +/-inf -> +/-DBL_MAX), like `jnp.nan_to_num(nlls)` (:218) */
 } odeu_ekf_io;
 
 /* Scratch size for the dynamically scheduled variant of odeu_ekf_run (0 if it does not apply). */

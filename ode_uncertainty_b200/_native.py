@@ -47,7 +47,7 @@ class EkfIO(C.Structure):
         ("workspace_bytes", C.c_int64),
         ("xT", _dp), ("epsT", _dp), ("PT", _dp), ("yhatT", _dp), ("ST", _dp), ("nll", _dp),
         ("tT", _dp), ("out_t", _dp), ("out_x", _dp), ("out_eps", _dp), ("out_P", _dp),
-        ("out_yhat", _dp), ("out_S", _dp),
+        ("out_yhat", _dp), ("out_S", _dp), ("cov_scale_batch", _dp), ("nll_nan_to_num", C.c_int32),
     ]
 
 

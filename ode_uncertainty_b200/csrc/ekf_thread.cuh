@@ -35,6 +35,8 @@ struct EkfArgs {
   const double* ys;       // nullable when has_obs == 0
   const unsigned char* flags;
   const long long* ymap;
+  const double* scale_b;  // nullable: per-trajectory cov_scale (calibration sweep)
+  int nan_to_num;         // per-step NLL terms through nan_to_num
   double* xT; double* epsT; double* PT; double* yhatT; double* ST; double* nll; double* tT;
   double* out_t; double* out_x; double* out_eps; double* out_P; double* out_yhat; double* out_S;
   // small shared matrices, by value (constant bank)
@@ -99,9 +101,19 @@ struct Segment {
   double* ws;               // [n + n*n + 1][B] state, then t per block of 32 trajectories
 };
 
+// jnp.nan_to_num of one log-likelihood term (calibration sweep, :218 of the calibration script)
+ODEU_HD double nll_term(double v, int nan_to_num) {
+  if (!nan_to_num) return v;
+  if (v != v) return 0.0;
+  if (v > 1.7976931348623157e308) return 1.7976931348623157e308;
+  if (v < -1.7976931348623157e308) return -1.7976931348623157e308;
+  return v;
+}
+
 template <class Ode, class Tab, int KC, int LK>
 ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long b, const Segment& sg) {
   constexpr int n = Ode::NX;
+  const double cov_scale = a.scale_b ? a.scale_b[b] : a.cov_scale;
   constexpr int NP = Ode::NP;
   constexpr int U = (n <= 4) ? n : 1;
   const long long B = a.B;
@@ -173,7 +185,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
       }
     }
     propagate_cov<n>(J, P);
-    add_process_noise<n>(a.noise_mode, a.cov_fn, a.cov_scale, eps, a.GQ, P);
+    add_process_noise<n>(a.noise_mode, a.cov_fn, cov_scale, eps, a.GQ, P);
 #pragma unroll U
     for (int i = 0; i < n; ++i) x[i] = xn[i];
     t = t + h;  // accumulated like rksolver.py:145 (stage times depend on it)
@@ -194,7 +206,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 #pragma unroll U
         for (int l = 0; l < n; ++l)
           if (l < L) y[l] = a.ys_per_traj ? a.ys[(oi * L + l) * B + b] : a.ys[oi * L + l];
-        nll += correct_step<n>(L, a.H, a.R, y, x, P, sink);
+        nll += nll_term(correct_step<n>(L, a.H, a.R, y, x, P, sink), a.nan_to_num);
         obs_fresh = true;
       }
     } else if constexpr (LK > 0) {
@@ -204,7 +216,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 #pragma unroll
         for (int l = 0; l < LK; ++l)
           y[l] = a.ys_per_traj ? a.ys[(oi * LK + l) * B + b] : a.ys[oi * LK + l];
-        nll += correct_step_lead<n, LK>(a.R, y, x, P, sink);
+        nll += nll_term(correct_step_lead<n, LK>(a.R, y, x, P, sink), a.nan_to_num);
         obs_fresh = true;
       }
     }

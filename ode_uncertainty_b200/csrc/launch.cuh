@@ -49,6 +49,7 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
   a.x0 = io.x0; a.P0 = io.P0; a.theta = io.theta; a.ys = io.ys;
   a.flags = io.correct_flags; a.ymap = (const long long*)io.xy_index_map;
   a.xT = io.xT; a.epsT = io.epsT; a.PT = io.PT; a.yhatT = io.yhatT; a.ST = io.ST; a.nll = io.nll;
+  a.scale_b = io.cov_scale_batch; a.nan_to_num = io.nll_nan_to_num;
   a.tT = io.tT;
   a.out_t = io.out_t; a.out_x = io.out_x; a.out_eps = io.out_eps; a.out_P = io.out_P;
   a.out_yhat = io.out_yhat; a.out_S = io.out_S;

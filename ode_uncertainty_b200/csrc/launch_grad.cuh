@@ -25,6 +25,7 @@ int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad
   if (io.L < 0 || io.L > n) { set_error("odeu_ekf_grad_run: L=%d outside [0, n=%d]", io.L, n); return -1; }
   if (!io.x0 || !io.P0_sqrt) { set_error("odeu_ekf_grad_run: x0 and a shared P0_sqrt are required"); return -1; }
   if (io.P0) { set_error("odeu_ekf_grad_run: per-trajectory P0 is not supported"); return -1; }
+  if (gp && (io.cov_scale_batch || io.nll_nan_to_num)) { set_error("odeu_ekf_grad_run: the calibration-sweep options are served by odeu_ekf_run"); return -1; }
   if (gp && (g.p_opt < 1 || g.p_opt > ODEU_MAX_GRAD || !g.idx || !g.grad)) {
     set_error("odeu_ekf_grad_run: need 1..%d parameter indices and a grad buffer", ODEU_MAX_GRAD);
     return -1;
@@ -83,7 +84,7 @@ template <class Ode>
 constexpr bool coop_eligible_static() { return Ode::NX > 4 && Ode::NX <= 16; }
 template <class Ode>
 bool coop_eligible(const odeu_ekf_io& io) {
-  return coop_eligible_static<Ode>() && 3 * io.L <= Ode::NX && !io.P0 && io.save_interval == 0 &&
+  return coop_eligible_static<Ode>() && 3 * io.L <= Ode::NX && !io.cov_scale_batch && !io.nll_nan_to_num && !io.P0 && io.save_interval == 0 &&
          !io.skip_predict && !io.epsT && !io.yhatT && !io.ST && !io.tT;
 }
 
@@ -123,7 +124,7 @@ template <class Ode, class Tab, class S>
 bool rows_eligible(const odeu_ekf_io& io) {
   if constexpr (rows_static_ok<Ode, Tab, S>()) {
     static const bool off = getenv("ODEU_NO_ROWS") != nullptr;   // A/B switch for measurements
-    return !off && io.L <= ROWS_LMAX && !io.P0 && io.save_interval == 0 && !io.skip_predict && !io.epsT &&
+    return !off && io.L <= ROWS_LMAX && !io.cov_scale_batch && !io.nll_nan_to_num && !io.P0 && io.save_interval == 0 && !io.skip_predict && !io.epsT &&
            !io.yhatT && !io.ST && !io.tT;
   } else {
     return false;

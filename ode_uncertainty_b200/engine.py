@@ -93,6 +93,7 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             xy_index_map: Optional[torch.Tensor] = None, save_interval: int = 0,
             save_keys=("t", "x", "eps", "P", "y_hat", "S"), want_final: bool = True,
             skip_predict: bool = False, dynamic: bool = True, minimal: bool = False,
+            cov_scale_batch: Optional[torch.Tensor] = None, nll_nan_to_num: bool = False,
             stream: Optional[torch.cuda.Stream] = None) -> EkfResult:
     """Run T EKF steps for a batch of trajectories.
 
@@ -152,6 +153,11 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
     io.correct_flags, io.xy_index_map = _dev(flags_k), _dev(map_k)
     io.save_interval = int(save_interval)
     io.skip_predict = int(bool(skip_predict))
+    scale_k = None
+    if cov_scale_batch is not None:      # calibration sweep: one covariance-update scale per trajectory
+        _require_cuda(cov_scale_batch, "cov_scale_batch")
+        scale_k = cov_scale_batch.to(torch.float64).reshape(B).contiguous()
+    io.cov_scale_batch, io.nll_nan_to_num = _dev(scale_k), int(bool(nll_nan_to_num))
     ws = None
     if dynamic and save_interval == 0 and not skip_predict and P0_k is None:
         wsb = int(N.lib().odeu_ekf_workspace_bytes(plan.handle, B, int(T)))

@@ -189,6 +189,53 @@ def run_filter(output: Optional[str] = None, filter_builder=None, solver_builder
 
 
 # ------------------------------------------------------------------------------------------------
+def calibration(output: Optional[str] = None, filter_builder=None, solver_builder=None, ode_builder=None,
+                x0="[[1.0, 1.0]]", P0=None, t0: float = 0.0, tN: float = 80.0, ts_y=None, ys_x=None,
+                y_path: Optional[str] = None, measurement_matrix=None, obs_noise_var: float = 1e-3,
+                min_noise_log: float = -8.0, max_noise_log: float = 0.0, num_noise_levels: int = 100,
+                device="cuda") -> Dict[str, np.ndarray]:
+    """`main()` of scripts/run_calibration_conrad_baseline_calibration.py:31-160: the filter's
+    log-likelihood (mean over ALL steps of the nan_to_num'ed per-step terms, :216-220) for
+    `num_noise_levels` static process-noise levels (`StaticDiagonalCovarianceUpdate`, scale =
+    noise level, :126-142) and for the configured error-driven covariance update (:143-154).
+    The reference scans the noise levels one after the other; here they are the batch axis of ONE
+    launch (one trajectory per level, per-trajectory scale).  Returns the reference's datasets
+    `noise_levels`, `nll_conrad`, `nll_ours` (:156-158)."""
+    from .covariance_update_functions import StaticDiagonalCovarianceUpdate
+    if measurement_matrix is None:
+        raise ValueError("Measurement matrix is required!")
+    dev = torch.device(device)
+    n = ode_builder.state_dim
+    x0_built = ode_builder.build_initial_value(_arr(x0), ode_builder.params).reshape(-1)
+    P0_sqrt = np.eye(n) * 1e-12 if P0 is None else np.linalg.cholesky(_arr(P0))
+    if y_path is not None:
+        dat = np.load(y_path)
+        ts_y, ys_x = dat["t"], dat["x"]
+    h = solver_builder.h
+    num_steps, flags, ymap = observation_schedule(t0, tN, h, ts_y)
+    H = _arr(measurement_matrix)
+    L = H.shape[0]
+    assert H.shape[1] == n, "Invalid measurement matrix!"
+    ys = np.einsum("ij,tj->ti", H, _arr(ys_x).reshape(-1, n))
+    levels = np.logspace(min_noise_log, max_noise_log, num_noise_levels, endpoint=True)
+    kw = dict(t0=float(t0), P0_sqrt=P0_sqrt, theta_shared=ode_builder.flat_params(ode_builder.params), H=H,
+              R_sqrt=np.eye(L) * obs_noise_var ** 0.5, ys=torch.as_tensor(ys).to(dev),
+              correct_flags=torch.as_tensor(flags.astype(np.uint8)).to(dev),
+              xy_index_map=torch.as_tensor(ymap).to(dev), want_final=False, nll_nan_to_num=True)
+    static_fb = type(filter_builder)(static_cov_update_fn_builder=StaticDiagonalCovarianceUpdate(1.0),
+                                     disable_cov_update=filter_builder.disable_cov_update)
+    plan_s = _plan_for(static_fb, solver_builder, ode_builder, use_static_cov_fn=True)
+    xb = torch.as_tensor(np.repeat(x0_built[None, :], num_noise_levels, axis=0)).to(dev)
+    r = ekf_run(plan_s, xb, num_steps, cov_scale_batch=torch.as_tensor(levels).to(dev), **kw)
+    plan_o = _plan_for(filter_builder, solver_builder, ode_builder)
+    r_o = ekf_run(plan_o, xb[:1], num_steps, **kw)
+    out = {"noise_levels": levels, "nll_conrad": r.nll.cpu().numpy() / num_steps,
+           "nll_ours": float(r_o.nll[0]) / num_steps}
+    if output is not None:
+        np.savez(output, **out)
+    return out
+
+
 def param_layout(ode_builder):
     """Index bookkeeping between JAX's flattening of the parameter dict (sorted keys,
     `ravel_pytree`) and the builder-order `theta` of the C ABI.

@@ -1,0 +1,104 @@
+"""Config front end: YAML files with the reference's `class_path` / `init_args`
+trees (structure of configs/ekf_trajectory_conrad_baseline/rkf45/lorenz.yaml and
+configs/params/lotkavolterra4.yaml) select the B200 plugins."""
+import os
+
+import numpy as np
+import pytest
+
+from ode_uncertainty_b200 import cli
+
+C1_YAML = """
+output: {out}
+filter_builder:
+  class_path: src.filters.SQRT_EKF
+  init_args:
+    cov_update_fn_builder:
+      class_path: src.covariance_update_functions.DiagonalCovarianceUpdate
+      init_args:
+        scale: 1.0
+    static_cov_update_fn_builder:
+      class_path: src.covariance_update_functions.StaticDiagonalCovarianceUpdate
+      init_args:
+        scale: 1.0
+solver_builder:
+  class_path: src.solvers.RKF45
+  init_args:
+    step_size: 0.01
+ode_builder:
+  class_path: src.ode.Lorenz
+x0: '[[1.0, 1.0, 1.0]]'
+P0: null
+t0: 0.0
+tN: 1.0
+y_path: null
+measurement_matrix: '[[1, 0, 0], [0, 1, 0], [0, 0, 1]]'
+obs_noise_var: 0.0
+save_interval: 1
+disable_pbar: false
+"""
+
+
+def test_config_tree_builds_the_b200_plugins(tmp_path):
+    from ode_uncertainty_b200 import filters, ode, solvers
+    from ode_uncertainty_b200.covariance_update_functions import DiagonalCovarianceUpdate
+    p = tmp_path / "c1.yaml"
+    p.write_text(C1_YAML.format(out=str(tmp_path / "res" / "lorenz.h5")))
+    cfg = cli.load_config(str(p), {"tN": "2.5", "save_interval": "5"})
+    assert isinstance(cfg["filter_builder"], filters.SQRT_EKF)
+    assert isinstance(cfg["filter_builder"].cov_update_fn_builder, DiagonalCovarianceUpdate)
+    assert isinstance(cfg["solver_builder"], solvers.RKF45) and cfg["solver_builder"].h == 0.01
+    assert isinstance(cfg["ode_builder"], ode.Lorenz)
+    assert cfg["tN"] == 2.5 and cfg["save_interval"] == 5 and "disable_pbar" not in cfg
+    assert cfg["output"].endswith("lorenz.npz")
+
+
+def test_unknown_plugins_fail_loudly(tmp_path):
+    p = tmp_path / "bad.yaml"
+    p.write_text("solver_builder:\n  class_path: src.solvers.DiffraxSolverBuilder\n  init_args: {step_size: 0.01}\n")
+    with pytest.raises(ValueError, match="DiffraxSolverBuilder"):
+        cli.load_config(str(p))
+    p.write_text("ode_builder:\n  class_path: somewhere.else.Thing\n")
+    with pytest.raises(ValueError, match="no B200 plugin"):
+        cli.load_config(str(p))
+
+
+def test_nested_schedule_and_hh_builder(tmp_path):
+    from ode_uncertainty_b200 import noise_schedules, ode
+    p = tmp_path / "pe.yaml"
+    p.write_text("""
+gamma_noise_schedule:
+  class_path: src.noise_schedules.LinearDecaySchedule
+  init_args:
+    init_noise_log: -2.0
+    decay_rate: 3
+ode_builder:
+  class_path: src.ode.MultiCompartmentHodgkinHuxley
+  init_args:
+    model: reduced-1
+    num_compartments: 2
+params_range:
+  g_Na: [0.5, 80.0]
+num_processes: 4
+""")
+    cfg = cli.load_config(str(p))
+    assert isinstance(cfg["gamma_noise_schedule"], noise_schedules.LinearDecaySchedule)
+    assert cfg["gamma_noise_schedule"].step(1) == pytest.approx(1e-5)
+    assert isinstance(cfg["ode_builder"], ode.MultiCompartmentHodgkinHuxley) and cfg["ode_builder"].state_dim == 14
+    assert cfg["params_range"] == {"g_Na": [0.5, 80.0]} and "num_processes" not in cfg
+
+
+@pytest.mark.gpu
+def test_run_filter_from_yaml_equals_direct_call(tmp_path):
+    from ode_uncertainty_b200 import ode as O, runners, solvers as S
+    from ode_uncertainty_b200.filters import SQRT_EKF
+    out = tmp_path / "res" / "lorenz.h5"
+    p = tmp_path / "c1.yaml"
+    p.write_text(C1_YAML.format(out=str(out)))
+    res = cli.main(["run_filter", "--config", str(p)])
+    ref = runners.run_filter(filter_builder=SQRT_EKF(), solver_builder=S.RKF45(step_size=0.01), ode_builder=O.Lorenz(),
+                             x0="[[1.0, 1.0, 1.0]]", t0=0.0, tN=1.0, save_interval=1)
+    np.testing.assert_array_equal(res["x"], ref["x"])
+    np.testing.assert_array_equal(res["P"], ref["P"])
+    saved = np.load(str(out)[:-3] + ".npz")
+    assert saved["x"].shape == (101, 1, 1, 3) and set(["t", "x", "eps", "P_sqrt"]).issubset(saved.files)

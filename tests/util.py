@@ -71,7 +71,7 @@ def make_plan(**kw):
 def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, theta_shared=None,
             Q_sqrt=None, gamma_sqrt=0.0, H=None, R_sqrt=None, ys=None, ys_per_trajectory=False,
             correct_flags=None, xy_index_map=None, save_interval=0, segmented=False, dynamic=True,
-            minimal=False):
+            minimal=False, cov_scale_batch=None, nll_nan_to_num=False):
     """Returns dict(xT [B,n], epsT, PT [B,n,n], nll [B], tT, traj{t,x,eps,P,y_hat,S}).
     segmented (hostemu): replay the dynamic scheduler's (block, time-segment) items sequentially."""
     x0 = _np(x0)
@@ -85,7 +85,8 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
                     R_sqrt=R_sqrt, ys=tt(ys), ys_per_trajectory=ys_per_trajectory,
                     correct_flags=tt(correct_flags, torch.uint8),
                     xy_index_map=tt(xy_index_map, torch.int64), save_interval=save_interval,
-                    dynamic=dynamic, minimal=minimal)
+                    dynamic=dynamic, minimal=minimal, cov_scale_batch=tt(cov_scale_batch),
+                    nll_nan_to_num=nll_nan_to_num)
         torch.cuda.synchronize()
         c = lambda v: None if v is None else v.cpu().numpy()
         out = dict(xT=c(r.xT), epsT=c(r.epsT), PT=c(r.PT), nll=c(r.nll),
@@ -130,6 +131,9 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
         io.xy_index_map = _p(K(_np(xy_index_map, np.int64)))
     io.L = L
     io.save_interval = int(save_interval)
+    if cov_scale_batch is not None:
+        io.cov_scale_batch = _p(K(_np(cov_scale_batch).reshape(B)))
+    io.nll_nan_to_num = int(bool(nll_nan_to_num))
     if segmented:
         wsbuf = K(np.zeros((n + n * n + 1) * B + (B + 31) // 32 + 8))
         io.workspace, io.workspace_bytes = _p(wsbuf), wsbuf.nbytes

@@ -156,8 +156,12 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double av, doubl
                : "+d"(d0), "+d"(d1) : "d"(av), "d"(bv));
 }
 
+// SYM: the product is symmetric (P = M J^T = J P J^T): only tiles on and below the diagonal are
+// computed, the off-diagonal ones are stored twice (the mirrored store writes 64-byte runs).
+template <bool SYM>
 __global__ void __launch_bounds__(256) dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm,
                                                         double* __restrict__ C, const double* __restrict__ qd, int n) {
+  if (SYM && blockIdx.x > blockIdx.y) return;
   extern __shared__ __align__(16) double gsm[];
   double* As = gsm;                       // [2][GT][GLD]
   double* Bs = gsm + 2 * GT * GLD;        // [2][GT][GLD]
@@ -222,6 +226,10 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(const double* __restrict_
         if (row == col + 1) v1 += qd[b * n + row];
       }
       *reinterpret_cast<double2*>(Cb + (long long)row * n + col) = make_double2(v0, v1);
+      if (SYM && blockIdx.x < blockIdx.y) {
+        Cb[(long long)col * n + row] = v0;
+        Cb[(long long)(col + 1) * n + row] = v1;
+      }
     }
   }
 }
@@ -445,7 +453,8 @@ static int dense_run_tab(const odeu_plan& plan, const odeu_dense_io& io, cudaStr
   const size_t cor_smem = sizeof(double) * (3 * (size_t)n * DL + 2 * DL * DL + 2 * DL);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+    cudaFuncSetAttribute(dgemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+    cudaFuncSetAttribute(dgemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
     cudaFuncSetAttribute(dense_correct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
@@ -454,8 +463,8 @@ static int dense_run_tab(const odeu_plan& plan, const odeu_dense_io& io, cudaStr
   for (long long step = 0; step < io.T; ++step) {
     sa.t = t;
     lcao_jac_kernel<Tab><<<(unsigned)B, n, jac_smem, st>>>(sa);
-    dgemm_nt_kernel<<<ggrid, 256, gemm_smem, st>>>(J, io.P, M, nullptr, n);       // M = J P
-    dgemm_nt_kernel<<<ggrid, 256, gemm_smem, st>>>(M, J, io.P, qd, n);           // P = M J^T + Q
+    dgemm_nt_kernel<false><<<ggrid, 256, gemm_smem, st>>>(J, io.P, M, nullptr, n);      // M = J P
+    dgemm_nt_kernel<true><<<ggrid, 256, gemm_smem, st>>>(M, J, io.P, qd, n);            // P = M J^T + Q
     count_launch(); count_launch(); count_launch();
     if (io.L > 0) {
       ca.step = step;

@@ -1,32 +1,69 @@
-"""BASELINE config 4, reference-parity part: perturbed-solver particle ensemble,
-M particles, Lorenz-63, RKF45 h=0.01, T steps, Diagonal scale 1, particle 0 noise-free.
+"""BASELINE config 4: particle ensemble, M particles, Lorenz-63, RKF45 h=0.01,
+Diagonal scale 1, particle 0 noise-free.
 
-    python tools/bench_c4.py [M] [T]          (single GPU; shard M/G per GPU for G GPUs)
-"""
+    python tools/bench_c4.py [M] [T]                      reference-parity part (predict only), 1 GPU
+    python tools/bench_c4.py [M] [T] --bootstrap          + extension: weights every 10 steps (H = I,
+                                                          R = 1e-2), global log-sum-exp, systematic
+                                                          resampling when ESS < M/2
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/bench_c4.py M T [--bootstrap]
+Under torchrun the M particles are SHARDED over the ranks (strong scaling, config 4 is a fixed
+1M-particle ensemble); the random stream is keyed by global particle index, so the ensemble does not
+depend on G.  The bootstrap variant uses NCCL for the global steps only: all-reduce(max, sum) of
+the log-weights, all-gather of the partial sums, all-to-all of the surviving particles."""
 import os
 import sys
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from oracle import ref_cpp as RC  # noqa: E402  (data synthesis only)
 from ode_uncertainty_b200 import Plan, _native as N, pf_run  # noqa: E402
+from ode_uncertainty_b200 import distributed as D  # noqa: E402
+from ode_uncertainty_b200.particle_filter_ext import bootstrap_filter  # noqa: E402
 
-M = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-T = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
-dev = torch.device("cuda:0")
+pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+M = int(pos[0]) if len(pos) > 0 else 1_000_000
+T = int(pos[1]) if len(pos) > 1 else 5000
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
 plan = Plan(N.ODE_LORENZ, N.SOLVER_RKF45, 0.01)
-best = 1e9
-for _ in range(3):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    r = pf_run(plan, M, T, x0_shared=[1.0, 1.0, 1.0], seed=7, device=dev)
-    e1.record()
-    torch.cuda.synchronize()
-    best = min(best, e0.elapsed_time(e1) * 1e-3)
+lo, hi = D.shard_bounds(M, rank, world)
+
+
+def timed(fn, reps):
+    best, out = 1e9, None
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+        tt = D.allreduce_max(torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev))
+        best = min(best, float(tt.item()))
+    return best, out
+
+
+best, r = timed(lambda: pf_run(plan, hi - lo, T, x0_shared=[1.0, 1.0, 1.0], seed=7, particle_offset=lo, device=dev), 3)
 units = M * T
-x = r.xT
-print(f"C4 particle ensemble: M={M} T={T} {best*1e3:.1f} ms  {units/best/1e9:.2f} G particle-steps/s  "
-      f"{units/best*210/1e12:.2f} TFLOP/s alg (~210 flops/unit)  finite={bool(torch.isfinite(x).all())}  "
-      f"spread={x.std(0).tolist()}")
+if rank != 0:
+    sys.stdout = open(os.devnull, "w")
+print(f"C4 particle ensemble [{world} GPU(s), {hi - lo} particles on rank 0]: M={M} T={T} {best*1e3:.1f} ms  "
+      f"{units/best/1e9:.2f} G particle-steps/s  {units/best*210/1e12:.2f} TFLOP/s alg (~210 flops/unit)  "
+      f"finite={bool(torch.isfinite(r.xT).all())}")
+if "--bootstrap" in sys.argv:
+    xs, _ = RC.rk_run("Lorenz", "RKF45", 0.01, [1.0, 1.0, 1.0], T, theta=[10.0, 8.0 / 3, 28.0])
+    ys = xs[10::10] + np.random.default_rng(8).normal(0.0, 0.1, xs[10::10].shape)
+    best, out = timed(lambda: bootstrap_filter(plan, M, T, ys, 10, np.eye(3), np.eye(3) * 1e-2,
+                                               x0_shared=[1.0, 1.0, 1.0], seed=7, device=dev), 2)
+    print(f"C4 bootstrap filter (extension, no reference oracle): {best*1e3:.1f} ms  {units/best/1e9:.2f} G particle-steps/s  "
+          f"{T // 10} weight normalisations, {len(out['resampled'])} resampling exchanges, loglik={out['loglik']:.6f}")
+if world > 1:
+    dist.destroy_process_group()

@@ -401,6 +401,12 @@ def main():
         bytes_str = B * (Ts + 1) * (3 + 3 + 9) * 8
         extras["lorenz_streaming_save_every_step"] = {"traj_steps_per_s": B * Ts / t_str,
                                                       "hbm_write_GBps": bytes_str / t_str / 1e9}
+        # C1 (BASELINE config 1, the reference's own CPU-runnable case): ONE Lorenz trajectory,
+        # T = 5,000 steps, prediction only, every step saved - a latency case, not a throughput case
+        x1 = torch.ones(1, 3, dtype=torch.float64, device=dev)
+        t_c1 = timed(lambda: ekf_run(plans["Lorenz"], x1, 5000, P0_sqrt=np.eye(3) * 1e-12, save_interval=1), reps=2)
+        extras["c1_single_trajectory"] = {"ms": 1e3 * t_c1, "traj_steps_per_s": 5000 / t_c1,
+                                          "sample": "B=1, T=5000, save_interval=1 (configs/ekf_trajectory_conrad_baseline/rkf45/lorenz.yaml)"}
         extras["vdp_traj_steps_per_s"] = B * T / (np.mean(vdp_ms) * 1e-3)
         extras["lorenz_traj_steps_per_s"] = B * T / (np.mean(lorenz_ms) * 1e-3)
         # other BASELINE configs, bounded samples (not part of `value`): C3 Hodgkin-Huxley

@@ -157,3 +157,32 @@ def test_cooperative_kernel_on_gpu(name):
     np.testing.assert_allclose(coop["xT"], thr["xT"], rtol=1e-11, atol=1e-300)
     np.testing.assert_allclose(coop["PT"], thr["PT"], rtol=1e-9, atol=1e-12 * np.abs(thr["PT"]).max())
     assert abs(coop["nll"][0] - float(gold["nll"])) <= 1e-9 * abs(float(gold["nll"]))
+
+
+@pytest.mark.gpu
+def test_shared_memory_kernels_are_run_to_run_deterministic():
+    """compute-sanitizer is not available on the GPU pool, so a missing barrier in the row-parallel
+    kernel (15+ barrier intervals per step) is hunted the poor man's way: a race makes results depend
+    on warp timing, so repeated launches on a larger batch must agree BIT FOR BIT (and with the
+    sequential host replay of the same source, tests/test_parity_cpu.py)."""
+    import util as U
+    name = "c3_mhh_r1_rkf45_temper"
+    spec = cases.CASES[name]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    B = 700                                   # several CTAs per SM, ragged tail
+    rng = np.random.default_rng(0)
+    x0 = np.repeat(m["x0"].reshape(1, -1).numpy(), B, axis=0)
+    x0[:, 0] += rng.uniform(-2, 2, B)
+    x0[:, 7] += rng.uniform(-2, 2, B)
+    kw = dict(t0=m["t0"], P0_sqrt=m["P0s"].numpy(), Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5,
+              H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy(), correct_flags=m["flags"],
+              xy_index_map=m["ymap"])
+    runs = [U.run_ekf("gpu", plan, x0, m["T"], minimal=True, **kw) for _ in range(4)]
+    for r in runs[1:]:
+        for k in ("nll", "xT", "PT"):
+            np.testing.assert_array_equal(r[k], runs[0][k])
+    g = [U.run_grad("gpu", plan, x0[:64], m["T"], np.arange(4, 10), theta_shared=plan.default_params, **kw) for _ in range(3)]
+    for gi in g[1:]:
+        np.testing.assert_array_equal(gi[0], g[0][0])
+        np.testing.assert_array_equal(gi[1], g[0][1])

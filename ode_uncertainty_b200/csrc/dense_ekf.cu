@@ -23,6 +23,7 @@
 // ys [T_obs][L] (shared) or [T_obs][B][L].  Workspace: J, M [B][n][n] and the noise diagonal [B][n].
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 #include "plan.h"
 #include "tableaux.cuh"
@@ -139,8 +140,8 @@ __global__ void __launch_bounds__(512) lcao_jac_kernel(const DenseStepArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // Batched C = A B^T (+ diag), all n x n row-major per batch entry, n a multiple of 128.
-// CTA tile 128 x 128, 8 warps as 2 x 4, warp tile 64 x 32 = 8 x 4 DMMA m8n8k4 tiles
-// (64 accumulator doubles per lane); k chunks of 16 double-buffered with cp.async.
+// CTA tile 128 x 64 (default; 8 warps as 4 x 2, warp tile 32 x 32 = 4 x 4 DMMA m8n8k4 tiles, 2 CTAs
+// per SM) or 128 x 128 (2 x 4 warps of 64 x 32); k chunks of 16 double-buffered with cp.async.
 // Shared rows are padded to 20 doubles so every fragment load is bank-conflict free.
 constexpr int GT = 128, GK = 16, GLD = 20;
 
@@ -156,36 +157,46 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double av, doubl
                : "+d"(d0), "+d"(d1) : "d"(av), "d"(bv));
 }
 
-// SYM: the product is symmetric (P = M J^T = J P J^T): only tiles on and below the diagonal are
-// computed, the off-diagonal ones are stored twice (the mirrored store writes 64-byte runs).
-template <bool SYM>
-__global__ void __launch_bounds__(256) dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm,
-                                                        double* __restrict__ C, const double* __restrict__ qd, int n) {
-  if (SYM && blockIdx.x > blockIdx.y) return;
+// SYM: the product is symmetric (P = M J^T = J P J^T): only tiles on and below the diagonal block
+// row are computed, tiles entirely below it are stored twice (the mirrored store writes 64-byte runs).
+// CTA tile 128 x BN, WM x WN warps, warp tile (128 / WM) x (BN / WN).
+template <bool SYM, int BN, int WM, int WN>
+__global__ void __launch_bounds__(32 * WM * WN, (BN <= 64 ? 2 : 1))
+dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ C,
+                const double* __restrict__ qd, int n) {
+  const int bm = blockIdx.y * GT, bn = blockIdx.x * BN;
+  if (SYM && bn >= bm + GT) return;
+  const bool mirror = SYM && (bn + BN <= bm);
   extern __shared__ __align__(16) double gsm[];
   double* As = gsm;                       // [2][GT][GLD]
-  double* Bs = gsm + 2 * GT * GLD;        // [2][GT][GLD]
+  double* Bs = gsm + 2 * GT * GLD;        // [2][BN][GLD]
   const long long b = blockIdx.z;
-  const int bm = blockIdx.y * GT, bn = blockIdx.x * GT;
   const double* Ab = A + b * (long long)n * n + (long long)bm * n;
   const double* Bb = Bm + b * (long long)n * n + (long long)bn * n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;       // 2 x 4 warps
+  constexpr int NTHR = 32 * WM * WN;
+  constexpr int MT = GT / (8 * WM), NT = BN / (8 * WN);   // 8-row / 8-column MMA tiles per warp
+  const int wm = warp / WN, wn = warp % WN;
   const int lr = lane >> 2, lc = lane & 3;
 
-  double acc[8][4][2];
+  double acc[MT][NT][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   auto load_tiles = [&](int buf, int k0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ch = tid + 256 * q;          // 1024 16-byte chunks per tile
+    for (int q = 0; q < GT * 8 / NTHR; ++q) {
+      const int ch = tid + NTHR * q;         // 8 16-byte chunks per row
       const int row = ch >> 3, c2 = (ch & 7) * 2;
       cp_async16(As + ((buf * GT + row) * GLD + c2), Ab + (long long)row * n + k0 + c2);
-      cp_async16(Bs + ((buf * GT + row) * GLD + c2), Bb + (long long)row * n + k0 + c2);
+    }
+#pragma unroll
+    for (int q = 0; q < BN * 8 / NTHR; ++q) {
+      const int ch = tid + NTHR * q;
+      const int row = ch >> 3, c2 = (ch & 7) * 2;
+      cp_async16(Bs + ((buf * BN + row) * GLD + c2), Bb + (long long)row * n + k0 + c2);
     }
     cp_async_commit();
   };
@@ -197,41 +208,55 @@ __global__ void __launch_bounds__(256) dgemm_nt_kernel(const double* __restrict_
     if (kc + 1 < nk) { load_tiles(buf ^ 1, (kc + 1) * GK); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();
-    const double* Aw = As + (buf * GT + wm * 64 + lr) * GLD + lc;
-    const double* Bw = Bs + (buf * GT + wn * 32 + lr) * GLD + lc;
+    const double* Aw = As + (buf * GT + wm * (8 * MT) + lr) * GLD + lc;
+    const double* Bw = Bs + (buf * BN + wn * (8 * NT) + lr) * GLD + lc;
 #pragma unroll
     for (int kk = 0; kk < GK / 4; ++kk) {
-      double af[8], bf[4];
+      double af[MT], bf[NT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = Aw[i * 8 * GLD + kk * 4];
+      for (int i = 0; i < MT; ++i) af[i] = Aw[i * 8 * GLD + kk * 4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = Bw[j * 8 * GLD + kk * 4];
+      for (int j = 0; j < NT; ++j) bf[j] = Bw[j * 8 * GLD + kk * 4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     __syncthreads();
   }
   double* Cb = C + b * (long long)n * n;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = bm + wm * 64 + i * 8 + lr;
+  for (int i = 0; i < MT; ++i) {
+    const int row = bm + wm * (8 * MT) + i * 8 + lr;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = bn + wn * 32 + j * 8 + 2 * lc;
+    for (int j = 0; j < NT; ++j) {
+      const int col = bn + wn * (8 * NT) + j * 8 + 2 * lc;
       double v0 = acc[i][j][0], v1 = acc[i][j][1];
       if (qd) {
         if (row == col) v0 += qd[b * n + row];
         if (row == col + 1) v1 += qd[b * n + row];
       }
       *reinterpret_cast<double2*>(Cb + (long long)row * n + col) = make_double2(v0, v1);
-      if (SYM && blockIdx.x < blockIdx.y) {
+      if (mirror) {
         Cb[(long long)col * n + row] = v0;
         Cb[(long long)(col + 1) * n + row] = v1;
       }
     }
   }
+}
+
+template <int BN, int WM, int WN>
+static void launch_gemms(const double* J, double* P, double* M, const double* qd, int n, long long B, cudaStream_t st) {
+  const size_t smem = sizeof(double) * 2 * (GT + BN) * GLD;
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(dgemm_nt_kernel<false, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dgemm_nt_kernel<true, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    done = true;
+  }
+  const dim3 grid(n / BN, n / GT, (unsigned)B);
+  dgemm_nt_kernel<false, BN, WM, WN><<<grid, 32 * WM * WN, smem, st>>>(J, P, M, nullptr, n);   // M = J P
+  dgemm_nt_kernel<true, BN, WM, WN><<<grid, 32 * WM * WN, smem, st>>>(M, J, P, qd, n);          // P = M J^T + Q
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,22 +474,21 @@ static int dense_run_tab(const odeu_plan& plan, const odeu_dense_io& io, cudaStr
   sa.x = io.x; sa.eps = io.eps; sa.J = J; sa.qd = qd;
 
   const size_t jac_smem = sizeof(double) * (n + (size_t)Tab::S * D);
-  const size_t gemm_smem = sizeof(double) * 4 * GT * GLD;
   const size_t cor_smem = sizeof(double) * (3 * (size_t)n * DL + 2 * DL * DL + 2 * DL);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(dgemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
-    cudaFuncSetAttribute(dgemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
     cudaFuncSetAttribute(dense_correct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  const dim3 ggrid(n / GT, n / GT, (unsigned)B);
+  // measured on B200 (tools/bench_c5.py): 128 x 64 tiles at 2 CTAs/SM 2.56 ms/step, 128 x 128 tiles at
+  // 1 CTA/SM 2.74 ms/step (the second CTA hides the prologue / epilogue of the 16-chunk k loop)
+  static const bool narrow = getenv("ODEU_GEMM_BN128") == nullptr;
   double t = io.t0;
   for (long long step = 0; step < io.T; ++step) {
     sa.t = t;
     lcao_jac_kernel<Tab><<<(unsigned)B, n, jac_smem, st>>>(sa);
-    dgemm_nt_kernel<false><<<ggrid, 256, gemm_smem, st>>>(J, io.P, M, nullptr, n);      // M = J P
-    dgemm_nt_kernel<true><<<ggrid, 256, gemm_smem, st>>>(M, J, io.P, qd, n);            // P = M J^T + Q
+    if (narrow) launch_gemms<64, 4, 2>(J, io.P, M, qd, n, B, st);     // 128 x 64 tiles, 2 CTAs/SM
+    else launch_gemms<128, 2, 4>(J, io.P, M, qd, n, B, st);            // 128 x 128 tiles, 1 CTA/SM
     count_launch(); count_launch(); count_launch();
     if (io.L > 0) {
       ca.step = step;

@@ -15,9 +15,10 @@
 //   3. dgemm_nt_kernel      P = M J^T + Q  (Q diagonal: embedded error / static / tempered noise,
 //                           src/filters/sqrt_ekf.py:96-136)
 //   4. dense_correct_kernel measurement update for a component-selecting H (L <= 16 observed
-//                           states): S = P[h,h] + R, Cholesky, K = P[:,h] S^-1, x += K d,
-//                           P <- P - K (HP) - G K^T with G = PH^T - K S (Joseph form up to its
-//                           rounding-level residual), NLL term (src/utils.py:109-128)
+//                           states): S = P[h,h] + R, Cholesky, K = P[:,h] S^-1, x += K d, NLL term
+//                           (src/utils.py:109-128); emits U = [K G], V = [PH^T K], G = PH^T - K S
+//   5. dgemm_nt_kernel<UPD> P <- P - U V^T = P - K (HP) - G K^T (Joseph form up to its
+//                           rounding-level residual) as a k = 32 DMMA update, HBM-bound
 //
 // Layout (device, float64): x [B][n], P [B][n][n] row-major per trajectory, observations
 // ys [T_obs][L] (shared) or [T_obs][B][L].  Workspace: J, M [B][n][n] and the noise diagonal [B][n].
@@ -160,10 +161,13 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double av, doubl
 // SYM: the product is symmetric (P = M J^T = J P J^T): only tiles on and below the diagonal block
 // row are computed, tiles entirely below it are stored twice (the mirrored store writes 64-byte runs).
 // CTA tile 128 x BN, WM x WN warps, warp tile (128 / WM) x (BN / WN).
-template <bool SYM, int BN, int WM, int WN>
+// UPD: C <- C - A B^T with narrow operands (leading dimension ld, inner dimension kdim): the
+// rank-2L covariance update of the measurement step, P <- P - [K G] [PH^T K]^T.
+template <bool SYM, bool UPD, int BN, int WM, int WN>
 __global__ void __launch_bounds__(32 * WM * WN, (BN <= 64 ? 2 : 1))
 dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ C,
-                const double* __restrict__ qd, int n) {
+                const double* __restrict__ qd, int n, int ld, int kdim, const unsigned char* __restrict__ flag) {
+  if (UPD && flag && !*flag) return;
   const int bm = blockIdx.y * GT, bn = blockIdx.x * BN;
   if (SYM && bn >= bm + GT) return;
   const bool mirror = SYM && (bn + BN <= bm);
@@ -171,8 +175,8 @@ dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm, dou
   double* As = gsm;                       // [2][GT][GLD]
   double* Bs = gsm + 2 * GT * GLD;        // [2][BN][GLD]
   const long long b = blockIdx.z;
-  const double* Ab = A + b * (long long)n * n + (long long)bm * n;
-  const double* Bb = Bm + b * (long long)n * n + (long long)bn * n;
+  const double* Ab = A + b * (long long)n * ld + (long long)bm * ld;
+  const double* Bb = Bm + b * (long long)n * ld + (long long)bn * ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NTHR = 32 * WM * WN;
   constexpr int MT = GT / (8 * WM), NT = BN / (8 * WN);   // 8-row / 8-column MMA tiles per warp
@@ -180,28 +184,38 @@ dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm, dou
   const int lr = lane >> 2, lc = lane & 3;
 
   double acc[MT][NT][2];
+  double* Cb = C + b * (long long)n * n;
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NT; ++j) {
+      if (UPD) {   // accumulators start from C (loads overlap the tile copies); A enters negated
+        const double2 old = *reinterpret_cast<const double2*>(
+            Cb + (long long)(bm + wm * (8 * MT) + i * 8 + lr) * n + bn + wn * (8 * NT) + j * 8 + 2 * lc);
+        acc[i][j][0] = old.x;
+        acc[i][j][1] = old.y;
+      } else {
+        acc[i][j][0] = acc[i][j][1] = 0.0;
+      }
+    }
 
   auto load_tiles = [&](int buf, int k0) {
 #pragma unroll
     for (int q = 0; q < GT * 8 / NTHR; ++q) {
       const int ch = tid + NTHR * q;         // 8 16-byte chunks per row
       const int row = ch >> 3, c2 = (ch & 7) * 2;
-      cp_async16(As + ((buf * GT + row) * GLD + c2), Ab + (long long)row * n + k0 + c2);
+      cp_async16(As + ((buf * GT + row) * GLD + c2), Ab + (long long)row * ld + k0 + c2);
     }
 #pragma unroll
     for (int q = 0; q < BN * 8 / NTHR; ++q) {
       const int ch = tid + NTHR * q;
       const int row = ch >> 3, c2 = (ch & 7) * 2;
-      cp_async16(Bs + ((buf * BN + row) * GLD + c2), Bb + (long long)row * n + k0 + c2);
+      cp_async16(Bs + ((buf * BN + row) * GLD + c2), Bb + (long long)row * ld + k0 + c2);
     }
     cp_async_commit();
   };
 
-  const int nk = n / GK;
+  const int nk = kdim / GK;
   load_tiles(0, 0);
   for (int kc = 0; kc < nk; ++kc) {
     const int buf = kc & 1;
@@ -214,7 +228,7 @@ dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm, dou
     for (int kk = 0; kk < GK / 4; ++kk) {
       double af[MT], bf[NT];
 #pragma unroll
-      for (int i = 0; i < MT; ++i) af[i] = Aw[i * 8 * GLD + kk * 4];
+      for (int i = 0; i < MT; ++i) af[i] = UPD ? -Aw[i * 8 * GLD + kk * 4] : Aw[i * 8 * GLD + kk * 4];
 #pragma unroll
       for (int j = 0; j < NT; ++j) bf[j] = Bw[j * 8 * GLD + kk * 4];
 #pragma unroll
@@ -224,7 +238,6 @@ dgemm_nt_kernel(const double* __restrict__ A, const double* __restrict__ Bm, dou
     }
     __syncthreads();
   }
-  double* Cb = C + b * (long long)n * n;
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
     const int row = bm + wm * (8 * MT) + i * 8 + lr;
@@ -250,13 +263,26 @@ static void launch_gemms(const double* J, double* P, double* M, const double* qd
   const size_t smem = sizeof(double) * 2 * (GT + BN) * GLD;
   static bool done = false;
   if (!done) {
-    cudaFuncSetAttribute(dgemm_nt_kernel<false, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(dgemm_nt_kernel<true, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dgemm_nt_kernel<false, false, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dgemm_nt_kernel<true, false, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     done = true;
   }
   const dim3 grid(n / BN, n / GT, (unsigned)B);
-  dgemm_nt_kernel<false, BN, WM, WN><<<grid, 32 * WM * WN, smem, st>>>(J, P, M, nullptr, n);   // M = J P
-  dgemm_nt_kernel<true, BN, WM, WN><<<grid, 32 * WM * WN, smem, st>>>(M, J, P, qd, n);          // P = M J^T + Q
+  dgemm_nt_kernel<false, false, BN, WM, WN><<<grid, 32 * WM * WN, smem, st>>>(J, P, M, nullptr, n, n, n, nullptr);   // M = J P
+  dgemm_nt_kernel<true, false, BN, WM, WN><<<grid, 32 * WM * WN, smem, st>>>(M, J, P, qd, n, n, n, nullptr);          // P = M J^T + Q
+}
+// P <- P - U V^T, U = [K G], V = [PH^T K] ([B][n][2 DL]); skipped when *flag == 0
+static void launch_update(const double* U, const double* V, double* P, int n, long long B, const unsigned char* flag,
+                          cudaStream_t st) {
+  constexpr int BN = 64, WM = 4, WN = 2;
+  const size_t smem = sizeof(double) * 2 * (GT + BN) * GLD;
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(dgemm_nt_kernel<true, true, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    done = true;
+  }
+  const dim3 grid(n / BN, n / GT, (unsigned)B);
+  dgemm_nt_kernel<true, true, BN, WM, WN><<<grid, 32 * WM * WN, smem, st>>>(U, V, P, nullptr, n, 2 * 16, 2 * 16, flag);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,130 +298,146 @@ struct DenseCorrectArgs {
   const double* ys; int ys_per_traj;
   const unsigned char* flags; const long long* ymap;
   double* x; double* P; double* nll;
+  double* U; double* V;            // [B][n][2 DL]: [K G] and [PH^T K] for the rank-2L update GEMM
 };
 
-__global__ void __launch_bounds__(512) dense_correct_kernel(const DenseCorrectArgs a) {
+// Step 4a: one WARP per trajectory (lane = observation row): S = P[h,h] + R, Cholesky, innovation,
+// NLL term, S^-1 (lane l solves for column l).  The serial chains of the small factorisation run
+// in B independent warps side by side instead of stalling a whole CTA per trajectory.
+// Outputs per trajectory (workspace): Sw = [S | S^-1 | d] = 2 DL^2 + DL doubles.  With the zero-gain
+// guard (see ekf_core.cuh) S^-1 is stored as 0, so K = 0 follows without a branch downstream.
+constexpr int SW = 2 * DL * DL + DL;
+constexpr int SLD = DL + 1;
+
+__global__ void __launch_bounds__(256) dense_innov_kernel(const DenseCorrectArgs a, double* __restrict__ Sw) {
   if (!a.flags[a.step]) return;
-  extern __shared__ double csm[];
+  __shared__ double sh[8][2 * DL * SLD + 2 * DL];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long b = (long long)blockIdx.x * 8 + w;
+  if (b >= a.B) return;
   const int n = a.n, L = a.L;
-  double* Ph = csm;                 // [n][DL]   P H^T
-  double* Kk = Ph + n * DL;         // [n][DL]   gain
-  double* Gk = Kk + n * DL;         // [n][DL]   PH^T - K S
-  double* Sm = Gk + n * DL;         // [DL][DL]
-  double* Ls = Sm + DL * DL;        // [DL][DL]
-  double* dv = Ls + DL * DL;        // [DL] innovation
-  double* iv = dv + DL;             // [DL] 1 / Ls_ii
-  __shared__ int s_tiny;
+  double* Sm = sh[w];               // [DL][SLD]
+  double* Ls = Sm + DL * SLD;       // [DL][SLD]
+  double* dv = Ls + DL * SLD;       // [DL]
+  double* iv = dv + DL;             // [DL]
+  const double* Pb = a.P + b * (long long)n * n;
+  const long long oi = a.ymap[a.step];
+  const bool act = lane < L;
+  if (act) {
+    const int hl = a.hidx[lane];
+    for (int m = 0; m < L; ++m) Sm[lane * SLD + m] = Pb[(long long)hl * n + a.hidx[m]] + a.R[lane * L + m];
+    const double y = a.ys_per_traj ? a.ys[(oi * a.B + b) * L + lane] : a.ys[oi * L + lane];
+    dv[lane] = y - a.x[b * n + hl];                              // y_hat = H x
+  }
+  __syncwarp();
+  for (int c = 0; c < L; ++c) {          // Cholesky S = Ls Ls^T, lane = row
+    if (lane == c) {
+      double s = Sm[c * SLD + c];
+      for (int k = 0; k < c; ++k) s = fma(-Ls[c * SLD + k], Ls[c * SLD + k], s);
+      const double d = sqrt(s);
+      Ls[c * SLD + c] = d;
+      iv[c] = 1.0 / d;
+    }
+    __syncwarp();
+    if (lane > c && act) {
+      double v = Sm[lane * SLD + c];
+      for (int k = 0; k < c; ++k) v = fma(-Ls[lane * SLD + k], Ls[c * SLD + k], v);
+      Ls[lane * SLD + c] = v * iv[c];
+    }
+    __syncwarp();
+  }
+  // z = Ls^-1 d (column sweep), NLL term (src/utils.py:109-128), zero-gain guard
+  double r = act ? dv[lane] : 0.0, z = 0.0;
+  for (int c = 0; c < L; ++c) {
+    const double zc = __shfl_sync(0xffffffffu, r, c) * iv[c];
+    if (lane == c) z = zc;
+    if (lane > c && act) r = fma(-Ls[lane * SLD + c], zc, r);
+  }
+  bool tiny = true;
+  double part = 0.0;
+  if (act) {
+    part = 0.5 * z * z + log(fabs(Ls[lane * SLD + lane]));
+    for (int k = 0; k <= lane; ++k) tiny = tiny && (fabs(Ls[lane * SLD + k]) < 1e-16);
+  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  const bool all_tiny = __all_sync(0xffffffffu, tiny);
+  if (lane == 0) a.nll[b] += part + 0.5 * (double)L * 1.8378770664093453;
+  // S^-1 column `lane`: Ls Ls^T v = e_lane
+  double* out = Sw + b * SW;
+  if (act) {
+    double wv[DL], v[DL];
+    for (int i = 0; i < L; ++i) {
+      double s = (i == lane) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s = fma(-Ls[i * SLD + k], wv[k], s);
+      wv[i] = s * iv[i];
+    }
+    for (int i = L - 1; i >= 0; --i) {
+      double s = wv[i];
+      for (int k = i + 1; k < L; ++k) s = fma(-Ls[k * SLD + i], v[k], s);
+      v[i] = s * iv[i];
+    }
+    for (int m = 0; m < DL; ++m) {
+      out[m * DL + lane] = (m < L) ? Sm[m * SLD + lane] : 0.0;
+      out[DL * DL + m * DL + lane] = (m < L && !all_tiny) ? v[m] : 0.0;
+    }
+    out[2 * DL * DL + lane] = dv[lane];
+  } else if (lane < DL) {
+    for (int m = 0; m < DL; ++m) { out[m * DL + lane] = 0.0; out[DL * DL + m * DL + lane] = 0.0; }
+    out[2 * DL * DL + lane] = 0.0;
+  }
+}
+
+// Step 4b: thread (trajectory, state j): K_j = (P H^T)_j S^-1, G_j = (P H^T)_j - K_j S, x_j += K_j d;
+// emits U = [K G], V = [PH^T K] for the rank-2L update.  No serial section.
+__global__ void __launch_bounds__(512) dense_gain_kernel(const DenseCorrectArgs a, const double* __restrict__ Sw) {
+  if (!a.flags[a.step]) return;
+  __shared__ __align__(16) double sw[SW];
+  const int n = a.n, L = a.L;
   const int j = threadIdx.x;
   const long long b = blockIdx.x;
-  double* Pb = a.P + b * (long long)n * n;
-  const long long oi = a.ymap[a.step];
+  for (int e = j; e < SW; e += n) sw[e] = Sw[b * SW + e];
+  const double* Pb = a.P + b * (long long)n * n;
   double ph[DL];
 #pragma unroll
-  for (int l = 0; l < DL; ++l) {
-    ph[l] = (l < L) ? Pb[(long long)a.hidx[l] * n + j] : 0.0;   // row h_l of the symmetric P
-    Ph[j * DL + l] = ph[l];
-  }
-  const double xj = a.x[b * n + j];
-  if (j < L) {
-    const double y = a.ys_per_traj ? a.ys[(oi * a.B + b) * L + j] : a.ys[oi * L + j];
-    dv[j] = y - a.x[b * n + a.hidx[j]];                         // y_hat = H x
-  }
+  for (int l = 0; l < DL; ++l) ph[l] = (l < L) ? Pb[(long long)a.hidx[l] * n + j] : 0.0;   // row h_l of the symmetric P
+  double xn = a.x[b * n + j];
   __syncthreads();
-  for (int e = j; e < DL * DL; e += n) {
-    const int l = e / DL, m = e % DL;
-    Sm[e] = (l < L && m < L) ? Ph[a.hidx[m] * DL + l] + a.R[l * L + m] : 0.0;
-  }
-  __syncthreads();
-  if (j < 32) {       // Cholesky S = Ls Ls^T by one warp (lane = row), NLL term by lane 0
-    bool tiny = true;
-    for (int c = 0; c < L; ++c) {
-      if (j == c) {
-        double s = Sm[c * DL + c];
-        for (int k = 0; k < c; ++k) s = fma(-Ls[c * DL + k], Ls[c * DL + k], s);
-        const double d = sqrt(s);
-        Ls[c * DL + c] = d;
-        iv[c] = 1.0 / d;
-      }
-      __syncwarp();
-      if (j > c && j < L) {
-        double v = Sm[j * DL + c];
-        for (int k = 0; k < c; ++k) v = fma(-Ls[j * DL + k], Ls[c * DL + k], v);
-        Ls[j * DL + c] = v * iv[c];
-      }
-      __syncwarp();
-    }
-    if (j == 0) {
-      double quad = 0.0, logdet = 0.0, z[DL];
-      for (int i = 0; i < L; ++i) {
-        double s = dv[i];
-        for (int k = 0; k < i; ++k) s = fma(-Ls[i * DL + k], z[k], s);
-        z[i] = s * iv[i];
-        quad = fma(z[i], z[i], quad);
-        logdet += log(fabs(Ls[i * DL + i]));
-        for (int k = 0; k <= i; ++k) tiny = tiny && (fabs(Ls[i * DL + k]) < 1e-16);
-      }
-      a.nll[b] += 0.5 * quad + 0.5 * (double)L * 1.8378770664093453 + logdet;
-      s_tiny = tiny ? 1 : 0;     // zero-gain guard, intended meaning (see ekf_core.cuh)
-    }
-  }
-  __syncthreads();
-  // gain row j: K_j = PHt_j S^-1 (two triangular solves), G_j = PHt_j - K_j S
-  double kj[DL], w[DL];
+  const double* Sm = sw;
+  const double* Si = sw + DL * DL;
+  const double* dv = sw + 2 * DL * DL;
+  double kj[DL], g[DL];
 #pragma unroll
-  for (int l = 0; l < DL; ++l) {
-    if (l < L) {
-      double s = ph[l];
+  for (int l = 0; l < DL; ++l) { kj[l] = 0.0; g[l] = ph[l]; }
 #pragma unroll
-      for (int k = 0; k < DL; ++k) if (k < l) s = fma(-Ls[l * DL + k], w[k], s);
-      w[l] = s * iv[l];
+  for (int m = 0; m < DL; ++m) {
+#pragma unroll
+    for (int l = 0; l < DL; l += 2) {
+      const double2 si = *reinterpret_cast<const double2*>(Si + m * DL + l);
+      kj[l] = fma(ph[m], si.x, kj[l]);
+      kj[l + 1] = fma(ph[m], si.y, kj[l + 1]);
     }
   }
 #pragma unroll
-  for (int l = DL - 1; l >= 0; --l) {
-    if (l < L) {
-      double s = w[l];
+  for (int m = 0; m < DL; ++m) {
 #pragma unroll
-      for (int k = 0; k < DL; ++k) if (k > l && k < L) s = fma(-Ls[k * DL + l], kj[k], s);
-      kj[l] = s_tiny ? 0.0 : s * iv[l];
-    } else {
-      kj[l] = 0.0;
+    for (int l = 0; l < DL; l += 2) {
+      const double2 sm2 = *reinterpret_cast<const double2*>(Sm + m * DL + l);
+      g[l] = fma(-kj[m], sm2.x, g[l]);
+      g[l + 1] = fma(-kj[m], sm2.y, g[l + 1]);
     }
   }
-  double xn = xj;
 #pragma unroll
-  for (int l = 0; l < DL; ++l) {
-    double g = ph[l];
-    if (l < L) {
-#pragma unroll
-      for (int m = 0; m < DL; ++m) if (m < L) g = fma(-kj[m], Sm[m * DL + l], g);
-      xn = fma(kj[l], dv[l], xn);
-    }
-    Kk[j * DL + l] = kj[l];
-    Gk[j * DL + l] = (l < L) ? g : 0.0;
-  }
+  for (int l = 0; l < DL; ++l) xn = fma(kj[l], dv[l], xn);
   a.x[b * n + j] = xn;
-  __syncthreads();
-  // P[k][j] -= K_k . PHt_j + G_k . K_j   (column j, coalesced over j; K_k, G_k broadcast).
-  // Four rows per iteration and two partial sums per row: eight independent DFMA chains.
-  for (int k = 0; k < n; k += 4) {
-    double pv[4], sa[4], sb[4];
+  // P <- P - K (HP) - G K^T = P - [K G] [PH^T K]^T: done by the DMMA update kernel
+  double2* Ub = reinterpret_cast<double2*>(a.U + (b * n + j) * (long long)(2 * DL));
+  double2* Vb = reinterpret_cast<double2*>(a.V + (b * n + j) * (long long)(2 * DL));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { pv[u] = Pb[(long long)(k + u) * n + j]; sa[u] = 0.0; sb[u] = 0.0; }
-#pragma unroll
-    for (int l = 0; l < DL / 2; ++l) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double2 kv = reinterpret_cast<const double2*>(Kk + (k + u) * DL)[l];
-        const double2 gv = reinterpret_cast<const double2*>(Gk + (k + u) * DL)[l];
-        sa[u] = fma(kv.x, ph[2 * l], sa[u]);
-        sb[u] = fma(gv.x, kj[2 * l], sb[u]);
-        sa[u] = fma(kv.y, ph[2 * l + 1], sa[u]);
-        sb[u] = fma(gv.y, kj[2 * l + 1], sb[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) Pb[(long long)(k + u) * n + j] = pv[u] - (sa[u] + sb[u]);
+  for (int l = 0; l < DL; l += 2) {
+    Ub[l / 2] = make_double2(kj[l], kj[l + 1]);
+    Ub[(DL + l) / 2] = make_double2(g[l], g[l + 1]);
+    Vb[l / 2] = make_double2(ph[l], ph[l + 1]);
+    Vb[(DL + l) / 2] = make_double2(kj[l], kj[l + 1]);
   }
 }
 
@@ -415,6 +457,9 @@ static int dense_run_tab(const odeu_plan& plan, const odeu_dense_io& io, cudaStr
   double* qd = M + B * nn;
   double* gq = qd + B * n;          // [n]
   double* P0d = gq + n;             // [n][n] staging of the shared initial covariance
+  double* Uw = P0d + nn;            // [B][n][2 DL]
+  double* Vw = Uw + B * n * 2 * DL;
+  double* Sww = Vw + B * n * 2 * DL;   // [B][SW]
   // ---- fold the small host matrices
   std::vector<double> gqh(n, 0.0), R(DL * DL, 0.0);
   bool qany = false;
@@ -465,6 +510,7 @@ static int dense_run_tab(const odeu_plan& plan, const odeu_dense_io& io, cudaStr
     }
   ca.ys = io.ys; ca.ys_per_traj = io.ys_per_trajectory; ca.flags = io.correct_flags;
   ca.ymap = (const long long*)io.xy_index_map; ca.x = io.x; ca.P = io.P; ca.nll = io.nll;
+  ca.U = Uw; ca.V = Vw;
 
   DenseStepArgs sa;
   sa.D = D; sa.n = n; sa.B = B; sa.h = plan.desc.step_size;
@@ -474,12 +520,6 @@ static int dense_run_tab(const odeu_plan& plan, const odeu_dense_io& io, cudaStr
   sa.x = io.x; sa.eps = io.eps; sa.J = J; sa.qd = qd;
 
   const size_t jac_smem = sizeof(double) * (n + (size_t)Tab::S * D);
-  const size_t cor_smem = sizeof(double) * (3 * (size_t)n * DL + 2 * DL * DL + 2 * DL);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(dense_correct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
   // measured on B200 (tools/bench_c5.py): 128 x 64 tiles at 2 CTAs/SM 2.56 ms/step, 128 x 128 tiles at
   // 1 CTA/SM 2.74 ms/step (the second CTA hides the prologue / epilogue of the 16-chunk k loop)
   static const bool narrow = getenv("ODEU_GEMM_BN128") == nullptr;
@@ -492,8 +532,10 @@ static int dense_run_tab(const odeu_plan& plan, const odeu_dense_io& io, cudaStr
     count_launch(); count_launch(); count_launch();
     if (io.L > 0) {
       ca.step = step;
-      dense_correct_kernel<<<(unsigned)B, n, cor_smem, st>>>(ca);
-      count_launch();
+      dense_innov_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(ca, Sww);
+      dense_gain_kernel<<<(unsigned)B, n, 0, st>>>(ca, Sww);
+      launch_update(Uw, Vw, io.P, n, B, io.correct_flags + step, st);
+      count_launch(); count_launch(); count_launch();
     }
     t += sa.h;
   }
@@ -541,7 +583,7 @@ extern "C" {
 int64_t odeu_ekf_dense_workspace_bytes(const odeu_plan* plan, int64_t B) {
   if (!plan || B <= 0) return 0;
   const long long n = plan->n;
-  return (int64_t)sizeof(double) * (2 * B * n * n + B * n + n + n * n);
+  return (int64_t)sizeof(double) * (2 * B * n * n + B * n + n + n * n + 2 * B * n * 32 + B * (2 * 16 * 16 + 16));
 }
 int odeu_ekf_dense_run(const odeu_plan* plan, const odeu_dense_io* io, void* cuda_stream) {
   if (!plan || !io) { odeu::set_error("odeu_ekf_dense_run: null argument"); return -1; }

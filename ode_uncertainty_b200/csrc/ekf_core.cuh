@@ -15,6 +15,7 @@
 // `all(|chol(S)| < 1e-16)`; the oracle reports every step where the LAPACK-sign
 // version would differ.
 #pragma once
+#include <cstring>
 #include "dual.cuh"
 #include "tableaux.cuh"
 #include "odes.cuh"
@@ -427,9 +428,42 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
 // systems ('[[1, 0]]', identity, ...; configs/*/*.yaml).  Same mathematics as correct_step:
 // H P = first L rows of P, so the H products disappear; Cholesky pivots use rsqrt, all solves
 // multiply by the stored reciprocals, and sum(log Ls_ii) = 0.5 log(prod pivots) needs one log.
+// Running product of Cholesky pivots kept as mantissa x 2^exponent: sum_t sum_i log Ls_ii =
+// 0.5 log(prod_t prod_i pivot), so the FP64 `log` (about 35 instructions) is taken once per time
+// segment instead of once per step; per step it costs one DMUL and a few integer operations.
+struct LogProd {
+  double m;
+  int e;
+  ODEU_HD static long long to_bits(double v) {
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(v);
+#else
+    long long b; memcpy(&b, &v, sizeof(b)); return b;
+#endif
+  }
+  ODEU_HD static double from_bits(long long b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(b);
+#else
+    double v; memcpy(&v, &b, sizeof(v)); return v;
+#endif
+  }
+  ODEU_HD void reset() { m = 1.0; e = 0; }
+  ODEU_HD void mul(double piv) {            // piv: normal, positive (checked by the caller)
+    const long long bits = to_bits(m * piv);
+    e += (int)((bits >> 52) & 0x7ff) - 1023;
+    m = from_bits((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);   // mantissa in [1, 2)
+  }
+  ODEU_HD double flush() {                  // 0.5 log(product), then start over
+    const double r = 0.5 * (log(m) + (double)e * 0.6931471805599453);
+    reset();
+    return r;
+  }
+};
+
 template <int n, int L>
 ODEU_HD double correct_step_lead(const double* R, const double* y, double* x, double (*P)[n],
-                                 const ObsSink& sink) {
+                                 const ObsSink& sink, LogProd* lp = nullptr) {
   double d[L], Ls[L][L], inv[L], Smat[L][L];
 #pragma unroll
   for (int l = 0; l < L; ++l) {
@@ -479,7 +513,8 @@ ODEU_HD double correct_step_lead(const double* R, const double* y, double* x, do
   // the normal range (or a pivot is non-positive / NaN)
   double logdet;
   if (piv > 1e-290 && piv < 1e290) {
-    logdet = 0.5 * log(piv);
+    if (lp) { lp->mul(piv); logdet = 0.0; }     // log deferred to LogProd::flush()
+    else logdet = 0.5 * log(piv);
   } else {
     logdet = 0.0;
 #pragma unroll

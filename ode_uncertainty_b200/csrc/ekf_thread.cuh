@@ -121,6 +121,8 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 
   double x[n], eps[n], P[n][n], th[NP];
   double t, nll;
+  LogProd lp;              // deferred log-determinant terms of this segment
+  lp.reset();
   if (sg.first) {
 #pragma unroll U
     for (int i = 0; i < n; ++i) x[i] = a.x0[i * B + b];
@@ -216,7 +218,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 #pragma unroll
         for (int l = 0; l < LK; ++l)
           y[l] = a.ys_per_traj ? a.ys[(oi * LK + l) * B + b] : a.ys[oi * LK + l];
-        nll += nll_term(correct_step_lead<n, LK>(a.R, y, x, P, sink), a.nan_to_num);
+        nll += nll_term(correct_step_lead<n, LK>(a.R, y, x, P, sink, a.nan_to_num ? nullptr : &lp), a.nan_to_num);
         obs_fresh = true;
       }
     }
@@ -238,7 +240,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     for (int i = 0; i < n; ++i)
 #pragma unroll U
       for (int j = 0; j <= i; ++j) sg.ws[(n + i * n + j) * B + b] = P[i][j];
-    sg.ws[(n + n * n) * B + b] = nll;
+    sg.ws[(n + n * n) * B + b] = nll + lp.flush();
     if ((b & 31) == 0) sg.ws[(n + n * n + 1) * B + (b >> 5)] = t;
     return;
   }
@@ -254,7 +256,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 #pragma unroll U
       for (int j = 0; j < n; ++j) a.PT[(i * n + j) * B + b] = P[i][j];
   }
-  if (a.nll) a.nll[b] = nll;
+  if (a.nll) a.nll[b] = nll + lp.flush();
   if (b == 0 && a.tT) a.tT[0] = t;
 }
 

@@ -115,7 +115,8 @@ def test_particle_zero_is_plain_rk_and_ensemble_statistics():
 
 def test_dynamic_scheduler_equals_static_launch_bitwise():
     """Persistent (block, time-segment) scheduling vs one static launch at the benchmark batch
-    size: same arithmetic per trajectory, so every output is bit-identical."""
+    size: same arithmetic per trajectory, so the state is bit-identical; the NLL agrees to
+    rounding (its log-determinant part is a pivot product flushed once per segment)."""
     from ode_uncertainty_b200 import Plan, ekf_run, _native as N
     dev = torch.device("cuda:0")
     for ode_id, n in ((N.ODE_LORENZ, 3), (N.ODE_VAN_DER_POL, 2)):
@@ -130,8 +131,9 @@ def test_dynamic_scheduler_equals_static_launch_bitwise():
                   xy_index_map=torch.arange(T, device=dev))
         a = ekf_run(plan, x0, T, dynamic=True, **kw)
         b = ekf_run(plan, x0, T, dynamic=False, **kw)
-        for k in ("xT", "PT", "nll", "epsT", "yhatT", "ST"):
+        for k in ("xT", "PT", "epsT", "yhatT", "ST"):
             assert torch.equal(getattr(a, k), getattr(b, k)), k
+        assert torch.allclose(a.nll, b.nll, rtol=1e-12, atol=1e-12)
         assert float(a.tT) == float(b.tT)
         # prediction only as well
         a = ekf_run(plan, x0, T, dynamic=True)

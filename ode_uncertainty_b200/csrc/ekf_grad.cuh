@@ -46,6 +46,9 @@ struct GradArgs {
   // -2 last needed stage: accumulated straight into J)
   int rw_need[8], rw_slot[8], rw_last;
   double rw_ha[8][8], rw_hb1[8];   // h a_ij, h b1_j
+  // measurement matrix with unit rows (every matrix the reference ships): observed component of
+  // each row, valid when h_sel_all != 0
+  int h_sel[8], h_sel_all;
 };
 
 // Same step as rk_step_generic with ROLLED stage loops and the tableau read from the kernel

@@ -29,6 +29,7 @@
 // is replayed sequentially on the host by the test-only emulation (tests/host_emu.cu).
 #pragma once
 #include "ekf_coop.cuh"
+#include "vec2.cuh"
 
 namespace odeu {
 
@@ -134,11 +135,12 @@ struct RowThread {
   static_assert(Q * G == n, "rows = groups x classes");
 
   // ---- per-thread state
+  static constexpr int NL = lanes_of<S>::value;   // trajectories carried by one scalar
   int tl, g, q, r;
   int per;         // paired-layout offset of element r
-  long long b;
+  long long b[NL];
   int chunk;
-  bool active;
+  bool active[NL];
   double t;
   S x, epsr, nll;
   S fcur;          // k_i of the stage being evaluated (filed into kp[] with a static index)
@@ -175,19 +177,28 @@ struct RowThread {
     return bl(sm)[SM::o_ex + ((which * n + i) * LM + l) * TB];
   }
 
+  // `unit` = first unit of this lane slot; a scalar with NL lanes also carries unit + TB, ...
   ODEU_HD void init(const Args& a, long long unit, int tl_, int g_, int q_, S* sm) {
     tl = tl_; g = g_; q = q_; r = g * Q + q;
     per = (r / PR) * (TB * PR) + (r % PR);
     const long long total = a.B * (a.p_opt > 0 ? a.p_opt : 1);
-    active = unit < total;
-    b = active ? unit % a.B : 0;
-    chunk = active ? (int)(unit / a.B) : 0;
-    x = S(a.x0[r * a.B + b]);
+    chunk = 0;
+    x = S(0.0);
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      const long long un = unit + (long long)u * TB;
+      active[u] = un < total;
+      b[u] = active[u] ? un % a.B : 0;
+      if (u == 0) chunk = active[u] ? (int)(un / a.B) : 0;
+      lane_set(x, u, a.x0[r * a.B + b[u]]);
+    }
     epsr = S(0.0);
     nll = S(0.0);
     t = a.t0;
     for (int k = r; k < NP; k += n) {
-      S v = S(a.theta ? a.theta[k * a.B + b] : a.theta_shared[k]);
+      S v = S(0.0);
+#pragma unroll
+      for (int u = 0; u < NL; ++u) lane_set(v, u, a.theta ? a.theta[k * a.B + b[u]] : a.theta_shared[k]);
       seed_theta(a, k, v);
       THp(sm)[k * TB] = v;
     }
@@ -197,13 +208,13 @@ struct RowThread {
     for (int m = 0; m < n; ++m) Kreg[m] = S(0.0);
   }
   ODEU_HD void seed_theta(const Args& a, int k, S& v) {
-    if constexpr (!std::is_same<S, double>::value) {
+    if constexpr (is_gdual<S>::value) {
       if (chunk < a.p_opt && a.idx[chunk] == k) v.d[0] = 1.0;
     }
   }
   ODEU_HD void seed_x0(const Args& a) {
-    if constexpr (!std::is_same<S, double>::value) {
-      if (chunk < a.p_opt && a.x0_tan) x.d[0] = a.x0_tan[((long long)chunk * n + r) * a.B + b];
+    if constexpr (is_gdual<S>::value) {
+      if (chunk < a.p_opt && a.x0_tan) x.d[0] = a.x0_tan[((long long)chunk * n + r) * a.B + b[0]];
     }
   }
 
@@ -422,10 +433,14 @@ struct RowThread {
     if (!(a.noise_mode == NOISE_COVFN && a.cov_fn == COV_OUTER)) return;
     const S* d = DFp(sm);
     const S er = d[per];
-    double ss = 0.0;
+    S poison = S(0.0);
 #pragma unroll
-    for (int k = 0; k < n; ++k) { const double e = scalar_ops<S>::val(d[pe(k)]); ss += e * e; }
-    const double poison = (ss == 0.0) ? (ss / ss) : 0.0;
+    for (int u = 0; u < NL; ++u) {
+      double ss = 0.0;
+#pragma unroll
+      for (int k = 0; k < n; ++k) { const double e = lane_get(d[pe(k)], u); ss += e * e; }
+      lane_set(poison, u, (ss == 0.0) ? (ss / ss) : 0.0);
+    }
 #pragma unroll
     for (int k = 0; k < n; ++k) W[k] = W[k] + er * d[pe(k)] + poison;
   }
@@ -445,31 +460,43 @@ struct RowThread {
       }
     }
   }
-  ODEU_HD void phase_gain(const Args& a, const double* y, S* sm) {
+  ODEU_HD void phase_gain(const Args& a, const S* y, S* sm) {
     const int L = obs_dim(a);
     S Sm[LM][LM], Ls[LM][LM], inv[LM], z[LM];
     const S* xs = Xp(sm);
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
       if (l < L) {
-        S s = xs[0] * a.H[l * n];
+        if (a.h_sel_all) {     // H row l = unit vector: y_hat_l = x[h_l], S_lm = (P H^T)[h_l][m] + R_lm
+          const int hl = a.h_sel[l];
+          dvec[l] = y[l] - xs[hl * TB];
 #pragma unroll
-        for (int j = 1; j < n; ++j) s = s + xs[j * TB] * a.H[l * n + j];
-        dvec[l] = y[l] - s;
+          for (int m = 0; m < LM; ++m) {
+            if (m <= l) {
+              const S v = EX(sm, 0, hl, m) + a.R[l * L + m];
+              Sm[l][m] = v;
+              Sm[m][l] = v;
+            }
+          }
+        } else {
+          S s = xs[0] * a.H[l * n];
 #pragma unroll
-        for (int m = 0; m < LM; ++m) {
-          if (m <= l) {
-            S v = S(a.R[l * L + m]);
+          for (int j = 1; j < n; ++j) s = s + xs[j * TB] * a.H[l * n + j];
+          dvec[l] = y[l] - s;
 #pragma unroll
-            for (int i = 0; i < n; ++i) v = v + EX(sm, 0, i, m) * a.H[l * n + i];
-            Sm[l][m] = v;
-            Sm[m][l] = v;
+          for (int m = 0; m < LM; ++m) {
+            if (m <= l) {
+              S v = S(a.R[l * L + m]);
+#pragma unroll
+              for (int i = 0; i < n; ++i) v = v + EX(sm, 0, i, m) * a.H[l * n + i];
+              Sm[l][m] = v;
+              Sm[m][l] = v;
+            }
           }
         }
       }
     }
-    bool all_tiny = true;
-    S logdet = S(0.0), quad = S(0.0);
+    Mask2 all_tiny = mask_true();
 #pragma unroll
     for (int j = 0; j < LM; ++j) {
       if (j < L) {
@@ -479,8 +506,7 @@ struct RowThread {
         const S dj = d_sqrt(s);
         Ls[j][j] = dj;
         inv[j] = 1.0 / dj;
-        all_tiny = all_tiny && (fabs(scalar_ops<S>::val(dj)) < 1e-16);
-        logdet = logdet + d_log(d_abs(dj));
+        mask_and_tiny(all_tiny, dj);
 #pragma unroll
         for (int i = 0; i < LM; ++i) {
           if (i > j && i < L) {
@@ -489,22 +515,26 @@ struct RowThread {
             for (int k = 0; k < LM; ++k) if (k < j) v = v - Ls[i][k] * Ls[j][k];
             v = v * inv[j];
             Ls[i][j] = v;
-            all_tiny = all_tiny && (fabs(scalar_ops<S>::val(v)) < 1e-16);
+            mask_and_tiny(all_tiny, v);
           }
         }
       }
     }
+    if (r == 0) {   // the log-likelihood term is kept by ONE thread of the trajectory (its logs are not free)
+      S logdet = S(0.0), quad = S(0.0);
 #pragma unroll
-    for (int i = 0; i < LM; ++i) {
-      if (i < L) {
-        S s = dvec[i];
+      for (int i = 0; i < LM; ++i) {
+        if (i < L) {
+          S s = dvec[i];
 #pragma unroll
-        for (int k = 0; k < LM; ++k) if (k < i) s = s - Ls[i][k] * z[k];
-        z[i] = s * inv[i];
-        quad = quad + z[i] * z[i];
+          for (int k = 0; k < LM; ++k) if (k < i) s = s - Ls[i][k] * z[k];
+          z[i] = s * inv[i];
+          quad = quad + z[i] * z[i];
+          logdet = logdet + d_log(d_abs(Ls[i][i]));
+        }
       }
+      nll = nll + (quad * 0.5 + logdet + 0.5 * (double)L * 1.8378770664093453);
     }
-    if (r == 0) nll = nll + (quad * 0.5 + logdet + 0.5 * (double)L * 1.8378770664093453);
     S w[LM];
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
@@ -521,7 +551,7 @@ struct RowThread {
         S s = w[l];
 #pragma unroll
         for (int k = 0; k < LM; ++k) if (k > l && k < L) s = s - Ls[k][l] * Krow[k];
-        Krow[l] = all_tiny ? S(0.0) : s * inv[l];
+        Krow[l] = zero_where(all_tiny, s * inv[l]);
       }
     }
 #pragma unroll
@@ -555,15 +585,18 @@ struct RowThread {
     if constexpr (n & 1) pr[pe(n - 1)] = W[n - 1];
   }
   ODEU_HD void finish(const Args& a, double* PT, S* sm) {
-    if (!active) return;
-    if (chunk == 0) {
-      if (r == 0 && a.nll) a.nll[b] = scalar_ops<S>::val(nll);
-      if (a.xT) a.xT[r * a.B + b] = scalar_ops<S>::val(x);
-      if (PT)
-        for (int k = 0; k < n; ++k) PT[((long long)r * n + k) * a.B + b] = scalar_ops<S>::val(Prow(sm, r)[pe(k)]);
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      if (!active[u]) continue;
+      if (chunk == 0) {
+        if (r == 0 && a.nll) a.nll[b[u]] = lane_get(nll, u);
+        if (a.xT) a.xT[r * a.B + b[u]] = lane_get(x, u);
+        if (PT)
+          for (int k = 0; k < n; ++k) PT[((long long)r * n + k) * a.B + b[u]] = lane_get(Prow(sm, r)[pe(k)], u);
+      }
     }
-    if constexpr (!std::is_same<S, double>::value) {
-      if (r == 0 && a.grad && chunk < a.p_opt) a.grad[(long long)chunk * a.B + b] = nll.d[0];
+    if constexpr (is_gdual<S>::value) {
+      if (active[0] && r == 0 && a.grad && chunk < a.p_opt) a.grad[(long long)chunk * a.B + b[0]] = nll.d[0];
     }
   }
 };
@@ -578,7 +611,8 @@ ekf_rows_kernel(const __grid_constant__ GradArgs<Ode::NX, Ode::NP> a, double* PT
   S* sm = reinterpret_cast<S*>(smem_raw);
   RowThread<Ode, Tab, S, TB, LT> th;
   const int lane = threadIdx.x & 31;
-  th.init(a, (long long)blockIdx.x * TB + lane % TB, lane % TB, lane / TB, threadIdx.x >> 5, sm);
+  constexpr int NL = lanes_of<S>::value;
+  th.init(a, (long long)blockIdx.x * (TB * NL) + lane % TB, lane % TB, lane / TB, threadIdx.x >> 5, sm);
   __syncthreads();
   for (long long step = 0; step < a.T; ++step) {
 #pragma unroll 1
@@ -597,10 +631,16 @@ ekf_rows_kernel(const __grid_constant__ GradArgs<Ode::NX, Ode::NP> a, double* PT
     if (a.has_obs && a.flags[step]) {
       const long long oi = a.ymap[step];
       const int L = LT > 0 ? LT : a.L;
-      double y[ROWS_LMAX];
+      S y[ROWS_LMAX];
 #pragma unroll
-      for (int l = 0; l < ROWS_LMAX; ++l)
-        if (l < L) y[l] = a.ys_per_traj ? a.ys[(oi * L + l) * a.B + th.b] : a.ys[oi * L + l];
+      for (int l = 0; l < ROWS_LMAX; ++l) {
+        if (l < L) {
+          y[l] = S(0.0);
+#pragma unroll
+          for (int u = 0; u < NL; ++u)
+            lane_set(y[l], u, a.ys_per_traj ? a.ys[(oi * L + l) * a.B + th.b[u]] : a.ys[oi * L + l]);
+        }
+      }
       th.phase_pht(a, sm);
       __syncthreads();
       th.phase_gain(a, y, sm);

@@ -76,6 +76,17 @@ int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad
   }
   for (int k = 0; k < NP; ++k)
     a.theta_shared[k] = io.theta_shared ? io.theta_shared[k] : plan.theta_default[k];
+  a.h_sel_all = (io.L > 0 && io.L <= 8) ? 1 : 0;
+  for (int l = 0; l < 8; ++l) a.h_sel[l] = 0;
+  for (int l = 0; l < io.L && l < 8; ++l) {
+    int ones = 0, other = 0, at = 0;
+    for (int j = 0; j < n; ++j) {
+      if (io.H[l * n + j] == 1.0) { ++ones; at = j; }
+      else if (io.H[l * n + j] != 0.0) ++other;
+    }
+    if (ones == 1 && other == 0) a.h_sel[l] = at;
+    else a.h_sel_all = 0;
+  }
   return 0;
 }
 
@@ -140,7 +151,8 @@ int launch_rows_lt(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t strea
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes);
   if (e != cudaSuccess) { set_error("row kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
   const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
-  kern<<<(unsigned)((units + TB - 1) / TB), 32 * Ode::ROW_CLASSES, SM::bytes, stream>>>(a, PT);
+  constexpr int UPC = TB * lanes_of<S>::value;      // units per CTA
+  kern<<<(unsigned)((units + UPC - 1) / UPC), 32 * Ode::ROW_CLASSES, SM::bytes, stream>>>(a, PT);
   return 0;
 }
 
@@ -149,6 +161,19 @@ int launch_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) 
   if constexpr (rows_static_ok<Ode, Tab, S>()) {
     fill_rt_tableau<Tab>(a);
     fill_rows_schedule<Tab>(a);
+    // Experiment kept behind ODEU_ROWS_2WIDE=1: two trajectories per thread (V2d scalar), one CTA of
+    // 32 trajectories per SM.  Measured on B200 (tools/bench_c3.py, B = 4,096): 25.4 ms per 1,000
+    // steps against 22.1 ms for two co-resident one-wide CTAs - the second dependency chain does
+    // fill issue slots (a lone 2-wide CTA needs 1.6x, not 2x, the time of a lone 1-wide one), but
+    // 255 registers with 1.5 KB of spills lose to plain co-residency.
+    if constexpr (std::is_same<S, double>::value && std::is_same<Tab, TabRKF45>::value &&
+                  rows_static_ok<Ode, Tab, V2d>()) {
+      static const bool two_wide = getenv("ODEU_ROWS_2WIDE") != nullptr;
+      if (two_wide) {
+        if (a.L == Ode::ROW_GROUPS && a.has_obs) return launch_rows_lt<Ode, Tab, V2d, Ode::ROW_GROUPS>(a, PT, stream);
+        return launch_rows_lt<Ode, Tab, V2d, 0>(a, PT, stream);
+      }
+    }
     // the headline tableau gets the observation dimension at compile time (L = number of
     // compartments / 1: the measurement matrices of configs/params/hodgkinhuxley*.yaml)
     if constexpr (std::is_same<Tab, TabRKF45>::value) {

@@ -61,13 +61,14 @@ int emu_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
     fill_rows_schedule<Tab>(a);
     using Th = RowThread<Ode, Tab, S, TB, 0>;
     using SM = RowsSmem<Ode, Tab, S, TB>;
+    constexpr int UPC = TB * lanes_of<S>::value;       // units per CTA
     const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
     std::vector<S> sm((size_t)SM::total);
     std::vector<Th> th((size_t)n * TB);
-    for (long long cta = 0; cta < (units + TB - 1) / TB; ++cta) {
+    for (long long cta = 0; cta < (units + UPC - 1) / UPC; ++cta) {
       for (int k = 0; k < n * TB; ++k) {
         const int tl = k % TB, g = (k / TB) % Ode::ROW_GROUPS, q = k / (TB * Ode::ROW_GROUPS);
-        th[k].init(a, cta * TB + tl, tl, g, q, sm.data());
+        th[k].init(a, cta * UPC + tl, tl, g, q, sm.data());
       }
       for (long long step = 0; step < a.T; ++step) {
         for (int i = 0; i < a.rt_S; ++i) {
@@ -82,8 +83,12 @@ int emu_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
           const long long oi = a.ymap[step];
           for (auto& t : th) t.phase_pht(a, sm.data());
           for (auto& t : th) {
-            double y[ROWS_LMAX];
-            for (int l = 0; l < a.L; ++l) y[l] = a.ys_per_traj ? a.ys[(oi * a.L + l) * a.B + t.b] : a.ys[oi * a.L + l];
+            S y[ROWS_LMAX];
+            for (int l = 0; l < a.L; ++l) {
+              y[l] = S(0.0);
+              for (int u = 0; u < lanes_of<S>::value; ++u)
+                lane_set(y[l], u, a.ys_per_traj ? a.ys[(oi * a.L + l) * a.B + t.b[u]] : a.ys[oi * a.L + l]);
+            }
             t.phase_gain(a, y, sm.data());
           }
           for (auto& t : th) t.phase_update(a, sm.data());
@@ -103,6 +108,9 @@ int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
   if (rows_eligible<Ode, Tab, double>(io) && (plan.desc.ode_id != ODEU_ODE_HODGKIN_HUXLEY || plan.desc.ode_variant != 4)) {
     GradArgs<Ode::NX, Ode::NP> g;                 // same routing as odeu_ekf_run
     if (int rc = fill_grad_args<Ode>(plan, io, nullptr, g)) return rc;
+    if constexpr (std::is_same<Tab, TabRKF45>::value && rows_static_ok<Ode, Tab, V2d>()) {
+      if (getenv("ODEU_ROWS_2WIDE")) return emu_rows<Ode, Tab, V2d>(g, io.PT);       // same routing as launch_rows
+    }
     return emu_rows<Ode, Tab, double>(g, io.PT);
   }
   if constexpr (coop_eligible_static<Ode>()) {

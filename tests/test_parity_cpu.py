@@ -160,3 +160,34 @@ def test_cooperative_kernel_source_matches_oracle_and_thread_kernel(name):
     assert abs(coop["nll"][0] - float(gold["nll"])) <= 1e-9 * abs(float(gold["nll"]))
     np.testing.assert_allclose(coop["xT"][0], gold["x"][-1], rtol=1e-10)
     np.testing.assert_allclose(coop["PT"][0], gold["P"][-1], rtol=1e-9, atol=1e-12 * np.abs(gold["P"][-1]).max())
+
+
+def test_two_wide_row_kernel_source_is_bitwise_equal_to_one_wide():
+    """ODEU_ROWS_2WIDE=1 (two trajectories per thread through the V2d scalar, vec2.cuh): the same
+    statements on two lanes, so the replayed source must agree bit for bit with the one-wide
+    kernel.  Runs in subprocesses because the switch is read once per process."""
+    import subprocess
+    import sys
+    import tempfile
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+import cases, util as U
+spec = cases.CASES["c3_mhh_r1_rkf45_temper"]; m = cases.materialize(spec); plan = cases.make_plan_for(spec)
+B = 11
+x0 = np.repeat(m["x0"].reshape(1, -1).numpy(), B, axis=0); x0[1:, 0] += 0.3 * np.arange(1, B)
+kw = dict(t0=m["t0"], P0_sqrt=m["P0s"].numpy(), Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5, H=m["H"].numpy(),
+          R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy(), correct_flags=m["flags"], xy_index_map=m["ymap"])
+c = U.run_ekf("hostemu", plan, x0, m["T"], minimal=True, **kw)
+np.save(sys.argv[1], np.concatenate([c["nll"].ravel(), c["xT"].ravel(), c["PT"].ravel()]))
+'''
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        outs = []
+        for tag, env in (("one", {}), ("two", {"ODEU_ROWS_2WIDE": "1"})):
+            out = os.path.join(td, tag + ".npy")
+            e = dict(os.environ); e.pop("ODEU_ROWS_2WIDE", None); e.update(env)
+            subprocess.check_call([sys.executable, "-c", code, out], cwd=root, env=e)
+            outs.append(np.load(out))
+    np.testing.assert_array_equal(outs[0], outs[1])

@@ -28,7 +28,7 @@ import torch
 
 from .engine import ekf_grad_run
 from .noise_schedules import ExponentialDecaySchedule, NoiseSchedule
-from .runners import _arr, _plan_for, observation_schedule, param_layout
+from .runners import _arr, _plan_for, initial_value_and_tangent, observation_schedule, param_layout
 
 
 class BatchedObjective:
@@ -85,8 +85,8 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
              params_optimized: Optional[Dict[str, bool]] = None, P0=None, t0: float = 0.0, tN: float = 80.0,
              num_tempering_stages: int = 10, final_gamma_zero: bool = True, obs_noise_var: float = 0.1,
              gamma_noise_schedule: NoiseSchedule = ExponentialDecaySchedule(), lbfgs_maxiter: int = 200,
-             num_random_runs: int = 0, seed: int = 7, device="cuda", verbose: bool = False
-             ) -> Dict[str, np.ndarray]:
+             num_random_runs: int = 0, seed: int = 7, initial_state_parametrized: bool = False,
+             device="cuda", verbose: bool = False) -> Dict[str, np.ndarray]:
     """scripts/run_parameter_estimation.py:49-308 with the same keyword meaning (observations
     are passed as arrays `ts_y`, `ys_x` instead of an H5 path)."""
     from scipy.optimize import minimize
@@ -141,9 +141,14 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
             flat = np.repeat(default_sorted[None, :], len(runs), axis=0)
             flat[:, opt_idx_sorted] = Z * (hi - lo) + lo                 # inv_normalize (:735-742)
             theta = torch.as_tensor(flat[:, perm]).to(dev)
-            nll, g = ekf_grad_run(plan, x0_all[: len(runs)], num_steps, grad_idx_builder, t0=t0,
+            x0_b, x0_tan = x0_all[: len(runs)], None
+            if initial_state_parametrized:               # x0 = build_initial_value(V0, theta), :744-748
+                xb, tan = initial_value_and_tangent(ode_builder, _arr(x0), flat, opt_idx_sorted)
+                x0_b, x0_tan = torch.as_tensor(xb).to(dev), torch.as_tensor(tan).to(dev)
+            nll, g = ekf_grad_run(plan, x0_b, num_steps, grad_idx_builder, t0=t0,
                                   P0_sqrt=P0_sqrt, theta=theta, Q_sqrt=Q_sqrt, gamma_sqrt=gamma ** 0.5,
-                                  H=H, R_sqrt=R_sqrt, ys=ys_d, correct_flags=flags_d, xy_index_map=ymap_d)
+                                  H=H, R_sqrt=R_sqrt, ys=ys_d, correct_flags=flags_d, xy_index_map=ymap_d,
+                                  x0_tangent=x0_tan)
             return nll.cpu().numpy(), g.cpu().numpy() * (hi - lo)        # d/d theta_norm
         return batch_fn
 

@@ -236,6 +236,36 @@ def calibration(output: Optional[str] = None, filter_builder=None, solver_builde
     return out
 
 
+def initial_value_and_tangent(ode_builder, x0_raw, flat_sorted: np.ndarray, opt_idx_sorted: np.ndarray,
+                              rel_step: float = 1e-6):
+    """`initial_state_parametrized` (scripts/run_parameter_estimation.py:744-748): x0(theta) =
+    build_initial_value(x0_raw, theta) for every row of `flat_sorted` [B, P] (all parameters, JAX's
+    sorted-key order) and its derivative w.r.t. the optimised entries, d x0 / d theta_j [B, p_opt, n]
+    - the `x0_tangent` of odeu_ekf_grad_run.  build_initial_value is a cheap host function
+    (Hodgkin-Huxley steady-state gates, src/ode/hodgkin_huxley.py:251-281); its derivative is taken
+    by central differences with a relative step of 1e-6 (truncation error ~1e-12 relative)."""
+    keys_s, sizes, _ = param_layout(ode_builder)
+
+    def build(row):
+        pd, o = {}, 0
+        for k in keys_s:
+            pd[k] = row[o:o + sizes[k]].reshape(np.asarray(ode_builder.params[k]).shape)
+            o += sizes[k]
+        return ode_builder.build_initial_value(x0_raw, pd).reshape(-1)
+
+    B = flat_sorted.shape[0]
+    xb = np.stack([build(flat_sorted[b]) for b in range(B)])
+    tan = np.zeros((B, len(opt_idx_sorted), xb.shape[1]))
+    for b in range(B):
+        for j, k in enumerate(opt_idx_sorted):
+            hstep = rel_step * max(1.0, abs(flat_sorted[b, k]))
+            up, dn = flat_sorted[b].copy(), flat_sorted[b].copy()
+            up[k] += hstep
+            dn[k] -= hstep
+            tan[b, j] = (build(up) - build(dn)) / (2.0 * hstep)
+    return xb, tan
+
+
 def param_layout(ode_builder):
     """Index bookkeeping between JAX's flattening of the parameter dict (sorted keys,
     `ravel_pytree`) and the builder-order `theta` of the C ABI.

@@ -152,8 +152,26 @@ def run_nll_and_grad(spec):
 
     val, g = jax.value_and_grad(f)(pn)
     gflat, _ = ravel_pytree(g)          # sorted-key order, like the optimiser sees it
-    return dict(nll_fn=np.array(float(val)), grad_norm=gflat.numpy(), grad_names=np.array(sorted(keys)),
-                lo=ravel_pytree(lo)[0].numpy(), hi=ravel_pytree(hi)[0].numpy())
+    out = dict(nll_fn=np.array(float(val)), grad_norm=gflat.numpy(), grad_names=np.array(sorted(keys)),
+               lo=ravel_pytree(lo)[0].numpy(), hi=ravel_pytree(hi)[0].numpy())
+    # initial_state_parametrized=True (:744-748): x0 = build_initial_value(V0, theta) is a function of
+    # the parameters (Hodgkin-Huxley steady-state gates depend on V_T, V_x); evaluated at a point OFF
+    # the defaults so that x0(theta) differs from the fixed x0 of the case
+    name = spec["ode"]
+    if name.startswith("HodgkinHuxley/") or name.startswith("MultiHH/"):
+        nc = int(name.split("/")[2]) if name.startswith("MultiHH/") else 1
+        x0_raw = jnp.full((1, nc), -70.0)
+        pn_isp = {k: pn[k] + (0.07 if k in ("V_T", "V_x") else 0.0) for k in keys}
+
+        def f_isp(params_norm):
+            return run_pe.nll(m["T"], True, False, filter_predict, filter_correct, solver, ode,
+                              ob.build_initial_value, cov_update_fn, params_norm, copy.copy(st), x0_raw,
+                              m["H"], m["ys"], flags, ymap, lo, hi, opt, idx, ob.params)
+
+        val2, g2 = jax.value_and_grad(f_isp)(pn_isp)
+        out.update(nll_fn_isp=np.array(float(val2)), grad_norm_isp=ravel_pytree(g2)[0].numpy(),
+                   pn_isp=ravel_pytree(pn_isp)[0].numpy())
+    return out
 
 
 def sync_times_fixture():

@@ -79,3 +79,47 @@ def test_gradient_matches_finite_differences_lorenz_eps_branch():
         assert abs(g[0, j] - fd) <= 2e-5 * max(1.0, abs(fd)), (j, g[0, j], fd)
     base = U.run_ekf("hostemu", plan, x0, 40, theta_shared=th, **kw)["nll"][0]
     assert abs(nll[0] - base) <= 1e-10 * abs(base)
+
+
+# ---- initial_state_parametrized (scripts/run_parameter_estimation.py:744-748): x0 depends on theta
+ISP = ["hh_r4_rkf45_temper", "hh_r1_rkf45_temper", "c3_mhh_r1_rkf45_temper"]
+
+
+def _check_isp(backend, name, batch=1):
+    """Against the reference's own nll() with initial_state_parametrized=True and its reverse-mode
+    gradient (fixture keys *_isp), at a point off the defaults so that x0(theta) matters."""
+    ref = dict(np.load(os.path.join(cases.GOLDEN, f"ref_{name}.npz")))
+    if "grad_norm_isp" not in ref:
+        pytest.skip("fixture without the initial_state_parametrized gradient")
+    spec = cases.CASES[name]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    ob = REF_GRAD[name]()
+    keys_s, sizes, perm = runners.param_layout(ob)
+    theta_sorted = ref["pn_isp"] * (ref["hi"] - ref["lo"]) + ref["lo"]
+    x0_raw = np.full((1, 2 if name.startswith("c3") else 1), -70.0)
+    idx_sorted = np.arange(theta_sorted.size)
+    xb, tan = runners.initial_value_and_tangent(ob, x0_raw, np.repeat(theta_sorted[None], batch, 0), idx_sorted)
+    idx_builder = np.array([int(np.nonzero(perm == j)[0][0]) for j in range(perm.size)])
+    nll, g = U.run_grad(backend, plan, xb, m["T"], idx_builder, t0=m["t0"], P0_sqrt=m["P0s"].numpy(),
+                        theta_shared=theta_sorted[perm], Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5,
+                        H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy(), correct_flags=m["flags"],
+                        xy_index_map=m["ymap"], x0_tangent=tan)
+    assert abs(nll[batch - 1] - float(ref["nll_fn_isp"])) <= 1e-9 * abs(float(ref["nll_fn_isp"]))
+    g_norm = g[batch - 1] * (ref["hi"] - ref["lo"])
+    scale = np.max(np.abs(ref["grad_norm_isp"]))
+    np.testing.assert_allclose(g_norm, ref["grad_norm_isp"], rtol=1e-6, atol=1e-6 * scale)
+    # x0 really depends on the parameters here (steady-state gates move with V_T); its influence on
+    # the gradient is small because the filter forgets its initial condition within a few observations
+    assert np.abs(tan).max() > 1e-5 and np.abs(xb[0] - m["x0"].reshape(-1).numpy()).max() > 1e-6
+
+
+@pytest.mark.parametrize("name", ISP)
+def test_initial_state_parametrized_gradient_matches_reference(name):
+    _check_isp("hostemu", name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ISP)
+def test_cuda_initial_state_parametrized_gradient(name):
+    _check_isp("gpu", name, batch=5)

@@ -225,8 +225,9 @@ def rel_err(a, b, floor=0.0):
 
 def run_grad(backend, plan, x0, T, grad_idx, *, t0=0.0, P0_sqrt=None, theta=None, theta_shared=None,
              Q_sqrt=None, gamma_sqrt=0.0, H=None, R_sqrt=None, ys=None, correct_flags=None,
-             xy_index_map=None):
-    """Returns (nll [B], grad [B, p_opt]) from the product path (gpu) or the host-compiled source."""
+             xy_index_map=None, x0_tangent=None):
+    """Returns (nll [B], grad [B, p_opt]) from the product path (gpu) or the host-compiled source.
+    x0_tangent [B, p_opt, n]: d x0 / d theta_j (initial_state_parametrized)."""
     x0 = _np(x0)
     B, n = x0.shape
     if backend == "gpu":
@@ -236,7 +237,7 @@ def run_grad(backend, plan, x0, T, grad_idx, *, t0=0.0, P0_sqrt=None, theta=None
         nll, g = ekf_grad_run(plan, tt(x0), T, grad_idx, t0=t0, P0_sqrt=P0_sqrt, theta=tt(theta),
                               theta_shared=theta_shared, Q_sqrt=Q_sqrt, gamma_sqrt=gamma_sqrt, H=H,
                               R_sqrt=R_sqrt, ys=tt(ys), correct_flags=tt(correct_flags, torch.uint8),
-                              xy_index_map=tt(xy_index_map, torch.int64))
+                              xy_index_map=tt(xy_index_map, torch.int64), x0_tangent=tt(x0_tangent))
         torch.cuda.synchronize()
         return nll.cpu().numpy(), g.cpu().numpy()
     emu = hostemu()
@@ -272,6 +273,8 @@ def run_grad(backend, plan, x0, T, grad_idx, *, t0=0.0, P0_sqrt=None, theta=None
     io.nll = _p(nll)
     g = N.GradIO()
     g.p_opt, g.idx, g.grad = int(idx.size), _p(idx), _p(grad)
+    if x0_tangent is not None:
+        g.x0_tangent = _p(K(np.ascontiguousarray(_np(x0_tangent).transpose(1, 2, 0))))     # [p_opt][n][B]
     th = (C.c_double * plan.p)(*plan.default_params)
     rc = emu.hostemu_grad_run(C.byref(plan.desc), th, plan.p, C.byref(io), C.byref(g))
     if rc != 0:

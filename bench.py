@@ -61,12 +61,17 @@ def workload_inputs(system: str, B: int, T: int, rank: int):
     return dict(n=n, x_true0=x_true0, x0=x0, P0_sqrt=P0_sqrt, H=H, R_sqrt=R_sqrt, t0=t0)
 
 
-def observations(system: str, T: int, w):
-    """Shared observation sequence: the true trajectory (noise-free RK from x_true0, CPU
-    restatement) + N(0, 1e-3), default_rng(8)."""
-    from oracle import ref_cpp as RC
-    th = {"Lorenz": [10.0, 8.0 / 3, 28.0], "VanDerPol": [5.0]}[system]
-    xs, _ = RC.rk_run(system, "RKF45", 0.01, w["x_true0"], T, t0=w["t0"], theta=th)
+def observations(system: str, T: int, w, plan=None, dev=None):
+    """Shared observation sequence: the true trajectory (noise-free RK from x_true0) + N(0, 1e-3),
+    default_rng(8).  The GPU arm integrates it with the product path (`plan` given); the CPU legs
+    (`--impl reference`, cpu_baseline) with the oracle's RK, the only place they may use it."""
+    if plan is not None:
+        from ode_uncertainty_b200 import runners
+        xs = runners.solve_trajectory(plan, w["x_true0"], T, t0=w["t0"], device=dev)
+    else:
+        from oracle import ref_cpp as RC
+        th = {"Lorenz": [10.0, 8.0 / 3, 28.0], "VanDerPol": [5.0]}[system]
+        xs, _ = RC.rk_run(system, "RKF45", 0.01, w["x_true0"], T, t0=w["t0"], theta=th)
     rng = np.random.default_rng(8)
     return xs[1:] + rng.normal(0.0, 1e-3 ** 0.5, (T, w["n"]))
 
@@ -174,8 +179,7 @@ def run_reference_arm(args):
 def _other_configs(dev, timed):
     """Bounded samples of BASELINE configs 3 and 4 for the `extras` block."""
     import torch
-    from oracle import ref_cpp as RC
-    from ode_uncertainty_b200 import Plan, _native as N, ekf_grad_run, ekf_run, pf_run
+    from ode_uncertainty_b200 import Plan, _native as N, ekf_grad_run, ekf_run, pf_run, runners
     from ode_uncertainty_b200 import ode as O
     out = {}
     # C3: 2-compartment reduced-1 HH, n=14, L=2, p=12, B=4096 parameter sets
@@ -184,7 +188,7 @@ def _other_configs(dev, timed):
     B3, T3 = 4096, 1000
     th0 = ob.flat_params(ob.params)
     x0 = ob.build_initial_value(np.array([[-70.0, -70.0]]), ob.params).reshape(-1)
-    xs, _ = RC.rk_run("MultiHH/reduced-1/2", "RKF45", 0.01, x0, T3, theta=th0)
+    xs = runners.solve_trajectory(plan, x0, T3, theta_shared=th0, device=dev)
     rng = np.random.default_rng(621)
     ys = xs[1:][:, [0, 7]] + rng.normal(0, 0.1 ** 0.5, (T3, 2))
     names, off, o = list(ob.params), {}, 0
@@ -268,7 +272,7 @@ def main():
     for system, ode_id in (("Lorenz", N.ODE_LORENZ), ("VanDerPol", N.ODE_VAN_DER_POL)):
         plans[system] = Plan(ode_id=ode_id, solver_id=N.SOLVER_RKF45, step_size=0.01)
         w = workload_inputs(system, B, T, rank)
-        ys = observations(system, T, w)
+        ys = observations(system, T, w, plans[system], dev)
         w["x0_host"] = torch.from_numpy(w["x0"]).pin_memory()
         w["ys_host"] = torch.from_numpy(ys).pin_memory()
         w["x0_dev"] = w["x0_host"].to(dev)

@@ -19,8 +19,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import ref_cpp as RC  # noqa: E402  (data synthesis only)
-from ode_uncertainty_b200 import Plan, _native as N, ekf_grad_run, ekf_run  # noqa: E402
+from ode_uncertainty_b200 import Plan, _native as N, ekf_grad_run, ekf_run, runners  # noqa: E402
 from ode_uncertainty_b200 import ode as O  # noqa: E402
 
 import torch.distributed as dist  # noqa: E402
@@ -41,7 +40,7 @@ ob = O.MultiCompartmentHodgkinHuxley(model="reduced-1", num_compartments=2)
 plan = Plan(N.ODE_MULTI_HH, N.SOLVER_RKF45, 0.01, ode_variant=1, num_compartments=2, disable_cov_update=True)
 th0 = ob.flat_params(ob.params)
 x0 = ob.build_initial_value(np.array([[-70.0, -70.0]]), ob.params).reshape(-1)
-xs, _ = RC.rk_run("MultiHH/reduced-1/2", "RKF45", 0.01, x0, T, theta=th0)
+xs = runners.solve_trajectory(plan, x0, T, theta_shared=th0, device=dev)
 rng = np.random.default_rng(621)
 ys = xs[1:][:, [0, 7]] + rng.normal(0, 0.1 ** 0.5, (T, 2))
 # optimised parameters and ranges of configs/params/hodgkinhuxley6_c2_r1.yaml:42-58

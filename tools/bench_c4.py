@@ -21,8 +21,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import ref_cpp as RC  # noqa: E402  (data synthesis only)
-from ode_uncertainty_b200 import Plan, _native as N, pf_run  # noqa: E402
+from ode_uncertainty_b200 import Plan, _native as N, pf_run, runners  # noqa: E402
 from ode_uncertainty_b200 import distributed as D  # noqa: E402
 from ode_uncertainty_b200.particle_filter_ext import bootstrap_filter  # noqa: E402
 
@@ -61,7 +60,7 @@ print(f"C4 particle ensemble [{world} GPU(s), {hi - lo} particles on rank 0]: M=
       f"{units/best/1e9:.2f} G particle-steps/s  {units/best*210/1e12:.2f} TFLOP/s alg (~210 flops/unit)  "
       f"finite={bool(torch.isfinite(r.xT).all())}")
 if "--bootstrap" in sys.argv:
-    xs, _ = RC.rk_run("Lorenz", "RKF45", 0.01, [1.0, 1.0, 1.0], T, theta=[10.0, 8.0 / 3, 28.0])
+    xs = runners.solve_trajectory(plan, [1.0, 1.0, 1.0], T, device=dev)
     ys = xs[10::10] + np.random.default_rng(8).normal(0.0, 0.1, xs[10::10].shape)
     best, out = timed(lambda: bootstrap_filter(plan, M, T, ys, 10, np.eye(3), np.eye(3) * 1e-2,
                                                x0_shared=[1.0, 1.0, 1.0], seed=7, device=dev,

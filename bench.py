@@ -411,6 +411,9 @@ def main():
         t_c1 = timed(lambda: ekf_run(plans["Lorenz"], x1, 5000, P0_sqrt=np.eye(3) * 1e-12, save_interval=1), reps=2)
         extras["c1_single_trajectory"] = {"ms": 1e3 * t_c1, "traj_steps_per_s": 5000 / t_c1,
                                           "sample": "B=1, T=5000, save_interval=1 (configs/ekf_trajectory_conrad_baseline/rkf45/lorenz.yaml)"}
+        extras["launch_ms_min_median_max"] = {
+            "lorenz": [float(np.min(lorenz_ms)), float(np.median(lorenz_ms)), float(np.max(lorenz_ms))],
+            "vdp": [float(np.min(vdp_ms)), float(np.median(vdp_ms)), float(np.max(vdp_ms))]}
         extras["vdp_traj_steps_per_s"] = B * T / (np.mean(vdp_ms) * 1e-3)
         extras["lorenz_traj_steps_per_s"] = B * T / (np.mean(lorenz_ms) * 1e-3)
         # other BASELINE configs, bounded samples (not part of `value`): C3 Hodgkin-Huxley

@@ -134,6 +134,10 @@ typedef struct {
                                      (overrides the plan's cov_scale), or NULL */
   int32_t nll_nan_to_num;    /* 1: every per-step term passes through nan_to_num before it is added
                                 (NaN -> 0, +/-inf -> +/-DBL_MAX), like `jnp.nan_to_num(nlls)` (:218) */
+  /* ---- parameter_sensitivity (scripts/run_parameter_estimation.py:750-769): Q_sqrt = diag(w) per
+   * parameter set, w from odeu_param_sensitivity.  Replaces Q_sqrt; honoured by odeu_ekf_grad_run
+   * (and the NLL-only row kernels of the Hodgkin-Huxley family), rejected by the other kernels. */
+  const double* Q_sqrt_diag_batch;  /* DEVICE [n][B] or NULL */
 } odeu_ekf_io;
 
 /* Scratch size for the dynamically scheduled variant of odeu_ekf_run (0 if it does not apply). */
@@ -163,10 +167,34 @@ typedef struct {
   const double* x0_tangent;  /* DEVICE [p_opt][n][B] d x0 / d theta_j (initial_state_parametrized,
                                 run_parameter_estimation.py:744-748) or NULL = 0 */
   double* grad;              /* DEVICE [p_opt][B] d NLL / d theta_j */
+  const double* Q_sqrt_diag_tangent; /* DEVICE [p_opt][n][B] d w / d theta_j for io->Q_sqrt_diag_batch
+                                (w_tangent of odeu_param_sensitivity), or NULL = 0 */
 } odeu_grad_io;
 
 int odeu_ekf_grad_run(const odeu_plan* plan, const odeu_ekf_io* io, const odeu_grad_io* grad,
                       void* cuda_stream);
+
+/* Parameter-sensitivity weights of the process noise, replaces the `if parameter_sensitivity:` block
+ * of nll() (scripts/run_parameter_estimation.py:750-769): one solver step from (t0, x0),
+ *   w_i = sum_{k in idx} |d x1_i / d theta_k|,   w <- sqrt(n) w / |w|_2,   Q_sqrt = diag(w).
+ * The reference evaluates it inside the differentiated loss; w_tangent carries d w / d theta_j
+ * (second derivatives of the step; with x0_tangent also the dependence through
+ * initial_state_parametrized) for odeu_grad_io.Q_sqrt_diag_tangent.  Derivatives are w.r.t. the
+ * PHYSICAL parameters, like odeu_ekf_grad_run. */
+typedef struct {
+  int64_t B;
+  double t0;
+  const double* x0;          /* DEVICE [n][B] */
+  const double* theta;       /* DEVICE [p][B] or NULL = theta_shared / defaults */
+  const double* theta_shared;/* HOST   [p] or NULL = reference defaults */
+  int32_t p_opt;             /* number of optimised parameters, 1..32 */
+  const int32_t* idx;        /* HOST [p_opt] flat parameter indices */
+  const double* x0_tangent;  /* DEVICE [p_opt][n][B] or NULL */
+  double* w;                 /* DEVICE [n][B] out */
+  double* w_tangent;         /* DEVICE [p_opt][n][B] out, or NULL */
+} odeu_sens_io;
+
+int odeu_param_sensitivity(const odeu_plan* plan, const odeu_sens_io* io, void* cuda_stream);
 
 /* Large-state EKF (BASELINE config 5): the oscillator chain of src/ode/lcao.py:51-61 generalised to
  * D oscillators (plan: ode_id = ODEU_ODE_LCAO, ode_variant = D >= 64, n = 2 D a multiple of 128),

@@ -22,7 +22,7 @@ SYMBOLS = (
     "odeu_plan_num_params", "odeu_plan_default_params", "odeu_ekf_run", "odeu_pf_run",
     "odeu_launch_count", "odeu_last_error", "odeu_bench_dfma", "odeu_ode_rhs",
     "odeu_ekf_grad_run", "odeu_ekf_workspace_bytes", "odeu_pf_weight_update",
-    "odeu_ekf_dense_run", "odeu_ekf_dense_workspace_bytes",
+    "odeu_ekf_dense_run", "odeu_ekf_dense_workspace_bytes", "odeu_param_sensitivity",
 )
 
 
@@ -48,11 +48,20 @@ class EkfIO(C.Structure):
         ("xT", _dp), ("epsT", _dp), ("PT", _dp), ("yhatT", _dp), ("ST", _dp), ("nll", _dp),
         ("tT", _dp), ("out_t", _dp), ("out_x", _dp), ("out_eps", _dp), ("out_P", _dp),
         ("out_yhat", _dp), ("out_S", _dp), ("cov_scale_batch", _dp), ("nll_nan_to_num", C.c_int32),
+        ("Q_sqrt_diag_batch", _dp),
     ]
 
 
 class GradIO(C.Structure):
-    _fields_ = [("p_opt", C.c_int32), ("idx", _dp), ("x0_tangent", _dp), ("grad", _dp)]
+    _fields_ = [("p_opt", C.c_int32), ("idx", _dp), ("x0_tangent", _dp), ("grad", _dp),
+                ("Q_sqrt_diag_tangent", _dp)]
+
+
+class SensIO(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("t0", C.c_double), ("x0", _dp), ("theta", _dp), ("theta_shared", _dp),
+        ("p_opt", C.c_int32), ("idx", _dp), ("x0_tangent", _dp), ("w", _dp), ("w_tangent", _dp),
+    ]
 
 
 class DenseIO(C.Structure):
@@ -116,6 +125,8 @@ def lib() -> C.CDLL:
     L.odeu_ekf_dense_run.restype = C.c_int
     L.odeu_ekf_grad_run.argtypes = [C.c_void_p, C.POINTER(EkfIO), C.POINTER(GradIO), C.c_void_p]
     L.odeu_ekf_grad_run.restype = C.c_int
+    L.odeu_param_sensitivity.argtypes = [C.c_void_p, C.POINTER(SensIO), C.c_void_p]
+    L.odeu_param_sensitivity.restype = C.c_int
     L.odeu_ode_rhs.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]
     L.odeu_ode_rhs.restype = C.c_int

@@ -95,10 +95,9 @@ def main(argv=None) -> Dict[str, np.ndarray]:
         ap.error("overrides must be given as --key value pairs")
     overrides = {k[2:]: v for k, v in zip(rest[0::2], rest[1::2])}
     cfg = load_config(args.config, overrides)
-    if cfg.pop("parameter_sensitivity", False):
-        raise NotImplementedError("parameter_sensitivity=true is not served by the B200 path yet (DESIGN.md section 7)")
     if args.script != "run_parameter_estimation":
         cfg.pop("initial_state_parametrized", None)
+        cfg.pop("parameter_sensitivity", None)
     if isinstance(cfg.get("output"), str):
         os.makedirs(os.path.dirname(os.path.abspath(cfg["output"])), exist_ok=True)
     from . import estimation, runners

@@ -157,7 +157,13 @@ int odeu_ekf_grad_run(const odeu_plan* plan, const odeu_ekf_io* io, const odeu_g
                       void* cuda_stream) {
   if (!plan || !io || !grad) { set_error("odeu_ekf_grad_run: null argument"); return -1; }
   if (!plan->grad_launch) { set_error("odeu_ekf_grad_run: no gradient kernel for this plan"); return -2; }
-  return plan->grad_launch(*plan, *io, *grad, (cudaStream_t)cuda_stream);
+  return plan->grad_launch(*plan, io, grad, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int odeu_param_sensitivity(const odeu_plan* plan, const odeu_sens_io* io, void* cuda_stream) {
+  if (!plan || !io) { set_error("odeu_param_sensitivity: null argument"); return -1; }
+  if (!plan->grad_launch) { set_error("odeu_param_sensitivity: no gradient kernel for this plan"); return -2; }
+  return plan->grad_launch(*plan, nullptr, nullptr, io, (cudaStream_t)cuda_stream);
 }
 
 int odeu_ode_rhs(const odeu_plan* plan, int64_t B, double t, const double* x, const double* theta,

@@ -76,6 +76,16 @@ struct CoopThread {
     nll = S(0.0);
     t = a.t0;
   }
+  // (gamma_sqrt w_c)^2 of the per-trajectory diagonal Q (parameter_sensitivity); re-read every step
+  // (an L1/L2 hit) instead of living in registers for the whole run
+  ODEU_HD S q_own(const Args& a) const {
+    S wv = S(a.qdiag[c * a.B + b]);
+    if constexpr (!std::is_same<S, double>::value) {
+      if (chunk < a.p_opt && a.qdiag_tan) wv.d[0] = a.qdiag_tan[((long long)chunk * n + c) * a.B + b];
+    }
+    wv = wv * a.q_gamma;
+    return wv * wv;
+  }
   // parameter direction of this thread (gradient instantiation only)
   ODEU_HD void seed_direction(const Args& a) {
     if constexpr (!std::is_same<S, double>::value) {
@@ -116,10 +126,12 @@ struct CoopThread {
         for (int i = 0; i < n; ++i) Pcol[i] = Pcol[i] + (eps[i] * a.cov_scale) * (eps[c] * a.cov_scale);
       } else Pcol[c] = Pcol[c] + a.cov_scale * a.cov_scale;
     } else if (a.noise_mode == NOISE_EPS_PLUS_Q) {
-      for (int i = 0; i < n; ++i) Pcol[i] = Pcol[i] + a.GQ[i * n + c];
+      if (a.qdiag) Pcol[c] = Pcol[c] + q_own(a);
+      else for (int i = 0; i < n; ++i) Pcol[i] = Pcol[i] + a.GQ[i * n + c];
       Pcol[c] = Pcol[c] + eps[c] * eps[c];
     } else if (a.noise_mode == NOISE_Q_ONLY) {
-      for (int i = 0; i < n; ++i) Pcol[i] = Pcol[i] + a.GQ[i * n + c];
+      if (a.qdiag) Pcol[c] = Pcol[c] + q_own(a);
+      else for (int i = 0; i < n; ++i) Pcol[i] = Pcol[i] + a.GQ[i * n + c];
     }
     for (int i = 0; i < n; ++i) x[i] = xn[i];
     t = t + a.h;

@@ -32,6 +32,11 @@ struct GradArgs {
   const double* x0;              // [n][B]
   const double* x0_tan;          // [p_opt][n][B] d x0 / d theta_j, or null (= 0)
   const double* theta;           // [NP][B] or null
+  // per-trajectory diagonal Q_sqrt = diag(w) of parameter_sensitivity
+  // (run_parameter_estimation.py:750-769) and its parameter tangents; replaces GQ when set
+  const double* qdiag;           // [n][B] or null
+  const double* qdiag_tan;       // [p_opt][n][B] or null
+  double q_gamma;                // gamma_sqrt
   const double* ys; const unsigned char* flags; const long long* ymap;
   double* nll;                   // [B]
   double* grad;                  // [p_opt][B]
@@ -260,6 +265,20 @@ ODEU_HD void ekf_grad_trajectory(const GradArgs<Ode::NX, Ode::NP>& a, const long
       if (j < a.p_opt && a.idx[j] == k) th[k].d[q] = 1.0;
     }
   }
+  S qd[n];                       // (gamma_sqrt w_i)^2 when the per-trajectory diagonal Q is given
+  for (int i = 0; i < n; ++i) {
+    qd[i] = S(0.0);
+    if (a.qdiag) {
+      S wv = S(a.qdiag[i * B + b]);
+#pragma unroll
+      for (int q = 0; q < PC; ++q) {
+        const int j = chunk * PC + q;
+        if (a.qdiag_tan && j < a.p_opt) wv.d[q] = a.qdiag_tan[((long long)j * n + i) * B + b];
+      }
+      wv = wv * a.q_gamma;
+      qd[i] = wv * wv;
+    }
+  }
   double t = a.t0;
   const double h = a.h;
   S nll = S(0.0);
@@ -306,12 +325,15 @@ ODEU_HD void ekf_grad_trajectory(const GradArgs<Ode::NX, Ode::NP>& a, const long
       }
     } else if (a.noise_mode == NOISE_EPS_PLUS_Q) {
       for (int i = 0; i < n; ++i) {
-        for (int k = 0; k < n; ++k) P[i][k] = P[i][k] + a.GQ[i * n + k];
+        if (a.qdiag) P[i][i] = P[i][i] + qd[i];
+        else for (int k = 0; k < n; ++k) P[i][k] = P[i][k] + a.GQ[i * n + k];
         P[i][i] = P[i][i] + eps[i] * eps[i];
       }
     } else if (a.noise_mode == NOISE_Q_ONLY) {
-      for (int i = 0; i < n; ++i)
-        for (int k = 0; k < n; ++k) P[i][k] = P[i][k] + a.GQ[i * n + k];
+      for (int i = 0; i < n; ++i) {
+        if (a.qdiag) P[i][i] = P[i][i] + qd[i];
+        else for (int k = 0; k < n; ++k) P[i][k] = P[i][k] + a.GQ[i * n + k];
+      }
     }
     for (int i = 0; i < n; ++i) x[i] = xn[i];
     t = t + h;

@@ -410,13 +410,32 @@ struct RowThread {
       else if (a.cov_fn == COV_OUTER) DFp(sm)[per] = epsr * a.cov_scale;   // exchanged, added in phase_noise_outer
       else add_diag(S(a.cov_scale * a.cov_scale));
     } else if (a.noise_mode == NOISE_EPS_PLUS_Q) {
+      if (a.qdiag) add_diag(q_own(a));
+      else {
 #pragma unroll
-      for (int k = 0; k < n; ++k) W[k] = W[k] + a.GQ[r * n + k];
+        for (int k = 0; k < n; ++k) W[k] = W[k] + a.GQ[r * n + k];
+      }
       add_diag(epsr * epsr);
     } else if (a.noise_mode == NOISE_Q_ONLY) {
+      if (a.qdiag) add_diag(q_own(a));
+      else {
 #pragma unroll
-      for (int k = 0; k < n; ++k) W[k] = W[k] + a.GQ[r * n + k];
+        for (int k = 0; k < n; ++k) W[k] = W[k] + a.GQ[r * n + k];
+      }
     }
+  }
+  // (gamma_sqrt w_r)^2 of the per-trajectory diagonal Q (parameter_sensitivity,
+  // run_parameter_estimation.py:750-769); re-read every step (an L1/L2 hit) so that it costs no
+  // registers on the runs that do not use it
+  ODEU_HD S q_own(const Args& a) const {
+    S wv = S(0.0);
+#pragma unroll
+    for (int u = 0; u < NL; ++u) lane_set(wv, u, a.qdiag[r * a.B + b[u]]);
+    if constexpr (is_gdual<S>::value) {
+      if (chunk < a.p_opt && a.qdiag_tan) wv.d[0] = a.qdiag_tan[((long long)chunk * n + r) * a.B + b[0]];
+    }
+    wv = wv * a.q_gamma;
+    return wv * wv;
   }
   ODEU_HD void add_diag(const S& v) {
     // unconditional stores: a guarded `if (k == r)` store is turned into a dynamically indexed

@@ -36,6 +36,10 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
   if (!io.x0) { set_error("odeu_ekf_run: x0 is required"); return -1; }
   if (!io.P0 && !io.P0_sqrt) { set_error("odeu_ekf_run: P0 or P0_sqrt is required"); return -1; }
   if (io.save_interval < 0) { set_error("odeu_ekf_run: save_interval < 0"); return -1; }
+  if (io.Q_sqrt_diag_batch) {
+    set_error("odeu_ekf_run: the per-trajectory diagonal Q_sqrt (parameter_sensitivity) is served by odeu_ekf_grad_run");
+    return -1;
+  }
   if (io.L > 0 && (!io.H || !io.R_sqrt || !io.ys || !io.correct_flags || !io.xy_index_map)) {
     set_error("odeu_ekf_run: L > 0 needs H, R_sqrt, ys, correct_flags, xy_index_map");
     return -1;

@@ -1,6 +1,7 @@
 // Host launcher of the forward-mode gradient kernel (ekf_grad.cuh).
 #pragma once
 #include "ekf_rows.cuh"
+#include "sens.cuh"
 #include <cstdlib>
 #include "plan.h"
 
@@ -44,6 +45,7 @@ int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad
     a.idx[j] = g.idx[j];
   }
   a.x0 = io.x0; a.x0_tan = g.x0_tangent; a.theta = io.theta; a.ys = io.ys;
+  a.qdiag = io.Q_sqrt_diag_batch; a.qdiag_tan = gp ? g.Q_sqrt_diag_tangent : nullptr; a.q_gamma = io.gamma_sqrt;
   a.flags = io.correct_flags; a.ymap = (const long long*)io.xy_index_map;
   a.nll = io.nll; a.grad = g.grad; a.xT = io.xT;
   for (int i = 0; i < n * n; ++i) { a.P0s[i] = 0.0; a.GQ[i] = 0.0; a.H[i] = 0.0; a.R[i] = 0.0; }
@@ -53,8 +55,10 @@ int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad
       for (int k = 0; k < n; ++k) s += io.P0_sqrt[i * n + k] * io.P0_sqrt[j * n + k];
       a.P0s[i * n + j] = s;
     }
-  bool qany = false;
-  if (io.Q_sqrt) {
+  // per-trajectory diag(w): w >= 0 with |w| = sqrt(n), so any(Q_sqrt >= 1e-16) holds (a NaN w, which
+  // the reference would route to the no-Q branch, poisons the run here instead)
+  bool qany = io.Q_sqrt_diag_batch != nullptr;
+  if (io.Q_sqrt && !io.Q_sqrt_diag_batch) {
     for (int i = 0; i < n * n; ++i) qany = qany || (io.Q_sqrt[i] >= 1e-16);
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) {
@@ -198,7 +202,36 @@ int launch_coop(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) 
 }
 
 template <class Ode, class Tab>
-int launch_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g, cudaStream_t stream) {
+int launch_sens(const odeu_plan& plan, const odeu_sens_io& s, cudaStream_t stream) {
+  constexpr int NP = Ode::NP;
+  if (s.B <= 0 || !s.x0 || !s.w) { set_error("odeu_param_sensitivity: B > 0, x0 and w are required"); return -1; }
+  if (s.p_opt < 1 || s.p_opt > ODEU_MAX_GRAD || !s.idx) {
+    set_error("odeu_param_sensitivity: need 1..%d parameter indices", ODEU_MAX_GRAD);
+    return -1;
+  }
+  SensArgs<NP> a;
+  a.B = s.B; a.t0 = s.t0; a.h = plan.desc.step_size; a.p_opt = s.p_opt;
+  for (int j = 0; j < ODEU_MAX_GRAD; ++j) a.idx[j] = -1;
+  for (int j = 0; j < s.p_opt; ++j) {
+    if (s.idx[j] < 0 || s.idx[j] >= NP) { set_error("odeu_param_sensitivity: parameter index %d out of range", s.idx[j]); return -1; }
+    a.idx[j] = s.idx[j];
+  }
+  a.x0 = s.x0; a.x0_tan = s.x0_tangent; a.theta = s.theta; a.w = s.w; a.w_tan = s.w_tangent;
+  for (int k = 0; k < NP; ++k) a.theta_shared[k] = s.theta_shared ? s.theta_shared[k] : plan.theta_default[k];
+  dim3 grid((unsigned)((s.B + 63) / 64), (unsigned)(s.w_tangent ? s.p_opt : 1));
+  param_sens_kernel<Ode, Tab><<<grid, 64, 0, stream>>>(a);
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("odeu_param_sensitivity: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
+template <class Ode, class Tab>
+int launch_grad(const odeu_plan& plan, const odeu_ekf_io* iop, const odeu_grad_io* gp, const odeu_sens_io* sens,
+                cudaStream_t stream) {
+  if (sens) return launch_sens<Ode, Tab>(plan, *sens, stream);
+  const odeu_ekf_io& io = *iop;
+  const odeu_grad_io& g = *gp;
   using Cfg = GradCfg<Ode>;
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, &g, a)) return rc;

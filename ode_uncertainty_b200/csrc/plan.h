@@ -18,7 +18,8 @@ struct odeu_plan {
   int (*pf_launch)(const odeu_plan&, const odeu_pf_io&, cudaStream_t);
   int (*rhs_launch)(const odeu_plan&, long long, double, const double*, const double*, const double*,
                     double*, cudaStream_t);
-  int (*grad_launch)(const odeu_plan&, const odeu_ekf_io&, const odeu_grad_io&, cudaStream_t);
+  // gradient run, or (sens != null) the parameter-sensitivity weights of the same ODE x solver
+  int (*grad_launch)(const odeu_plan&, const odeu_ekf_io*, const odeu_grad_io*, const odeu_sens_io*, cudaStream_t);
   int (*coop_launch)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);   // null for small systems
 };
 
@@ -31,7 +32,7 @@ using EkfLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);
 using PfLaunchFn = int (*)(const odeu_plan&, const odeu_pf_io&, cudaStream_t);
 using RhsLaunchFn = int (*)(const odeu_plan&, long long, double, const double*, const double*,
                            const double*, double*, cudaStream_t);
-using GradLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, const odeu_grad_io&, cudaStream_t);
+using GradLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io*, const odeu_grad_io*, const odeu_sens_io*, cudaStream_t);
 using CoopLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);
 CoopLaunchFn resolve_coop_hh(int model, int solver);
 CoopLaunchFn resolve_coop_multi_hh(int model, int nc, int solver);

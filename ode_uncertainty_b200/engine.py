@@ -228,9 +228,12 @@ def ekf_grad_run(plan: Plan, x0: torch.Tensor, T: int, grad_idx, *, t0: float = 
                  gamma_sqrt: float = 0.0, H=None, R_sqrt=None, ys: Optional[torch.Tensor] = None,
                  ys_per_trajectory: bool = False, correct_flags: Optional[torch.Tensor] = None,
                  xy_index_map: Optional[torch.Tensor] = None, x0_tangent: Optional[torch.Tensor] = None,
+                 Q_sqrt_diag: Optional[torch.Tensor] = None, Q_sqrt_diag_tangent: Optional[torch.Tensor] = None,
                  stream: Optional[torch.cuda.Stream] = None):
     """NLL [B] and d NLL / d theta_j [B, p_opt] for the flat parameter indices `grad_idx`
-    (builder order) in one launch (`odeu_ekf_grad_run`).  x0_tangent [B, p_opt, n] optional."""
+    (builder order) in one launch (`odeu_ekf_grad_run`).  x0_tangent [B, p_opt, n] optional.
+    Q_sqrt_diag [B, n] (+ Q_sqrt_diag_tangent [B, p_opt, n]): per-parameter-set Q_sqrt = diag(w) of
+    `parameter_sensitivity` (see `param_sensitivity`); replaces Q_sqrt."""
     _require_cuda(x0, "x0")
     dev = x0.device
     B, n = x0.shape
@@ -262,11 +265,18 @@ def ekf_grad_run(plan: Plan, x0: torch.Tensor, T: int, grad_idx, *, t0: float = 
     x0t_k = None
     if x0_tangent is not None:
         x0t_k = x0_tangent.to(torch.float64).permute(1, 2, 0).contiguous()    # [p_opt][n][B]
+    qd_k = qdt_k = None
+    if Q_sqrt_diag is not None:
+        _require_cuda(Q_sqrt_diag, "Q_sqrt_diag")
+        qd_k = Q_sqrt_diag.to(torch.float64).t().contiguous()                 # [n][B]
+        if Q_sqrt_diag_tangent is not None:
+            qdt_k = Q_sqrt_diag_tangent.to(torch.float64).permute(1, 2, 0).contiguous()   # [p_opt][n][B]
     io = N.EkfIO()
     io.B, io.T, io.t0, io.L = B, int(T), float(t0), L
     io.x0, io.P0_sqrt = _dev(x0_k), _hp(P0s_h)
     io.theta, io.theta_shared = _dev(th_k), _hp(ths_h)
     io.Q_sqrt, io.gamma_sqrt = _hp(Q_h), float(gamma_sqrt)
+    io.Q_sqrt_diag_batch = _dev(qd_k)
     io.H, io.R_sqrt, io.ys = _hp(H_h), _hp(R_h), _dev(ys_k)
     io.ys_per_trajectory = int(bool(ys_per_trajectory))
     io.correct_flags, io.xy_index_map = _dev(flags_k), _dev(map_k)
@@ -275,11 +285,47 @@ def ekf_grad_run(plan: Plan, x0: torch.Tensor, T: int, grad_idx, *, t0: float = 
     io.nll = _dev(nll)
     g = N.GradIO()
     g.p_opt, g.idx, g.x0_tangent, g.grad = int(p_opt), idx.ctypes.data_as(C.c_void_p), _dev(x0t_k), _dev(grad)
+    g.Q_sqrt_diag_tangent = _dev(qdt_k)
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
         N.check(N.lib().odeu_ekf_grad_run(plan.handle, C.byref(io), C.byref(g), C.c_void_p(st.cuda_stream)),
                 "odeu_ekf_grad_run")
     return nll, grad.t()
+
+
+def param_sensitivity(plan: Plan, x0: torch.Tensor, grad_idx, *, t0: float = 0.0,
+                      theta: Optional[torch.Tensor] = None, theta_shared=None,
+                      x0_tangent: Optional[torch.Tensor] = None, want_tangent: bool = True,
+                      stream: Optional[torch.cuda.Stream] = None):
+    """The `parameter_sensitivity` weights of nll() (scripts/run_parameter_estimation.py:750-769):
+    w [B, n] with Q_sqrt = diag(w), and d w / d theta_j [B, p_opt, n] (physical parameters), from one
+    solver step at (t0, x0) (`odeu_param_sensitivity`)."""
+    _require_cuda(x0, "x0")
+    dev = x0.device
+    B, n = x0.shape
+    if n != plan.n:
+        raise ValueError(f"x0 has state dimension {n}, plan expects {plan.n}")
+    f64 = dict(dtype=torch.float64, device=dev)
+    idx = np.ascontiguousarray(np.asarray(grad_idx, dtype=np.int32))
+    p_opt = idx.size
+    x0_k = x0.to(torch.float64).t().contiguous()
+    th_k = None
+    if theta is not None:
+        _require_cuda(theta, "theta")
+        th_k = theta.to(torch.float64).t().contiguous()
+    ths_h = _host(theta_shared, (plan.p,)) if theta_shared is not None else None
+    x0t_k = None if x0_tangent is None else x0_tangent.to(torch.float64).permute(1, 2, 0).contiguous()
+    w = torch.zeros(n, B, **f64)
+    wt = torch.zeros(p_opt, n, B, **f64) if want_tangent else None
+    s = N.SensIO()
+    s.B, s.t0, s.x0, s.theta, s.theta_shared = B, float(t0), _dev(x0_k), _dev(th_k), _hp(ths_h)
+    s.p_opt, s.idx, s.x0_tangent = int(p_opt), idx.ctypes.data_as(C.c_void_p), _dev(x0t_k)
+    s.w, s.w_tangent = _dev(w), _dev(wt)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().odeu_param_sensitivity(plan.handle, C.byref(s), C.c_void_p(st.cuda_stream)),
+                "odeu_param_sensitivity")
+    return w.t(), (None if wt is None else wt.permute(2, 0, 1))
 
 
 @dataclass

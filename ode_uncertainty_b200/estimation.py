@@ -26,7 +26,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 import torch
 
-from .engine import ekf_grad_run
+from .engine import ekf_grad_run, param_sensitivity
 from .noise_schedules import ExponentialDecaySchedule, NoiseSchedule
 from .runners import _arr, _plan_for, initial_value_and_tangent, observation_schedule, param_layout
 
@@ -86,7 +86,7 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
              num_tempering_stages: int = 10, final_gamma_zero: bool = True, obs_noise_var: float = 0.1,
              gamma_noise_schedule: NoiseSchedule = ExponentialDecaySchedule(), lbfgs_maxiter: int = 200,
              num_random_runs: int = 0, seed: int = 7, initial_state_parametrized: bool = False,
-             device="cuda", verbose: bool = False) -> Dict[str, np.ndarray]:
+             parameter_sensitivity: bool = False, device="cuda", verbose: bool = False) -> Dict[str, np.ndarray]:
     """scripts/run_parameter_estimation.py:49-308 with the same keyword meaning (observations
     are passed as arrays `ts_y`, `ys_x` instead of an H5 path)."""
     from scipy.optimize import minimize
@@ -145,10 +145,13 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
             if initial_state_parametrized:               # x0 = build_initial_value(V0, theta), :744-748
                 xb, tan = initial_value_and_tangent(ode_builder, _arr(x0), flat, opt_idx_sorted)
                 x0_b, x0_tan = torch.as_tensor(xb).to(dev), torch.as_tensor(tan).to(dev)
+            qd = qd_tan = None
+            if parameter_sensitivity:                    # Q_sqrt = diag(w(theta)) inside the loss, :750-769
+                qd, qd_tan = param_sensitivity(plan, x0_b, grad_idx_builder, t0=t0, theta=theta, x0_tangent=x0_tan)
             nll, g = ekf_grad_run(plan, x0_b, num_steps, grad_idx_builder, t0=t0,
                                   P0_sqrt=P0_sqrt, theta=theta, Q_sqrt=Q_sqrt, gamma_sqrt=gamma ** 0.5,
                                   H=H, R_sqrt=R_sqrt, ys=ys_d, correct_flags=flags_d, xy_index_map=ymap_d,
-                                  x0_tangent=x0_tan)
+                                  x0_tangent=x0_tan, Q_sqrt_diag=qd, Q_sqrt_diag_tangent=qd_tan)
             return nll.cpu().numpy(), g.cpu().numpy() * (hi - lo)        # d/d theta_norm
         return batch_fn
 

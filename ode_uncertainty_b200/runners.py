@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .engine import Plan, ekf_run, pf_run
+from .engine import Plan, ekf_grad_run, ekf_run, param_sensitivity, pf_run
 
 
 # ------------------------------------------------------------------------------------------------
@@ -297,7 +297,8 @@ def param_layout(ode_builder):
 def ekf_nll(filter_builder, solver_builder, ode_builder, *, params_norm, params_min, params_max,
             params_optimized: Optional[Dict[str, bool]] = None, x0, P0_sqrt, t0: float, num_steps: int,
             measurement_matrix, ys, correct_flags, xy_index_map, R_sqrt, Q_sqrt, gamma_sqrt: float,
-            initial_state_parametrized: bool = False, device="cuda") -> torch.Tensor:
+            initial_state_parametrized: bool = False, parameter_sensitivity: bool = False,
+            device="cuda") -> torch.Tensor:
     """Batched `nll()` of scripts/run_parameter_estimation.py:685-796.
 
     params_norm: dict key -> [B, size] normalised values in [0, 1] for the optimised parameters
@@ -336,6 +337,16 @@ def ekf_nll(filter_builder, solver_builder, ode_builder, *, params_norm, params_
                        if x0_arr.size != plan.n else x0_arr.reshape(1, -1), B, axis=0)
     H = _arr(measurement_matrix)
     L = H.shape[0]
+    if parameter_sensitivity:                                           # :750-769: Q_sqrt = diag(w(theta))
+        gidx = np.argsort(perm)[opt_idx]                                # builder positions of the optimised entries
+        xb_d, th_d = torch.as_tensor(xb).to(dev), torch.as_tensor(theta).to(dev)
+        w, _ = param_sensitivity(plan, xb_d, gidx, t0=float(t0), theta=th_d, want_tangent=False)
+        nll, _ = ekf_grad_run(plan, xb_d, int(num_steps), gidx[:1], t0=float(t0), P0_sqrt=_arr(P0_sqrt), theta=th_d,
+                              gamma_sqrt=float(gamma_sqrt), H=H, R_sqrt=_arr(R_sqrt).reshape(L, L),
+                              ys=torch.as_tensor(_arr(ys)).to(dev),
+                              correct_flags=torch.as_tensor(_arr(correct_flags, np.uint8)).to(dev),
+                              xy_index_map=torch.as_tensor(_arr(xy_index_map, np.int64)).to(dev), Q_sqrt_diag=w)
+        return nll
     r = ekf_run(plan, torch.as_tensor(xb).to(dev), int(num_steps), t0=float(t0), P0_sqrt=_arr(P0_sqrt),
                 theta=torch.as_tensor(theta).to(dev), Q_sqrt=_arr(Q_sqrt), gamma_sqrt=float(gamma_sqrt),
                 H=H, R_sqrt=_arr(R_sqrt).reshape(L, L), ys=torch.as_tensor(_arr(ys)).to(dev),

@@ -154,6 +154,18 @@ def run_nll_and_grad(spec):
     gflat, _ = ravel_pytree(g)          # sorted-key order, like the optimiser sees it
     out = dict(nll_fn=np.array(float(val)), grad_norm=gflat.numpy(), grad_names=np.array(sorted(keys)),
                lo=ravel_pytree(lo)[0].numpy(), hi=ravel_pytree(hi)[0].numpy())
+    # parameter_sensitivity=True (:750-769): Q_sqrt = diag(w(theta)), w from |d x_1 / d theta| of one
+    # solver step, inside the differentiated loss.  Evaluated OFF the defaults.
+    pn_ps = {k: pn[k] + 0.05 for k in keys}
+
+    def f_ps(params_norm):
+        return run_pe.nll(m["T"], False, True, filter_predict, filter_correct, solver, ode,
+                          ob.build_initial_value, cov_update_fn, params_norm, copy.copy(st), m["x0"],
+                          m["H"], m["ys"], flags, ymap, lo, hi, opt, idx, ob.params)
+
+    val3, g3 = jax.value_and_grad(f_ps)(pn_ps)
+    out.update(nll_fn_ps=np.array(float(val3)), grad_norm_ps=ravel_pytree(g3)[0].numpy(),
+               pn_ps=ravel_pytree(pn_ps)[0].numpy())
     # initial_state_parametrized=True (:744-748): x0 = build_initial_value(V0, theta) is a function of
     # the parameters (Hodgkin-Huxley steady-state gates depend on V_T, V_x); evaluated at a point OFF
     # the defaults so that x0(theta) differs from the fixed x0 of the case
@@ -171,6 +183,14 @@ def run_nll_and_grad(spec):
         val2, g2 = jax.value_and_grad(f_isp)(pn_isp)
         out.update(nll_fn_isp=np.array(float(val2)), grad_norm_isp=ravel_pytree(g2)[0].numpy(),
                    pn_isp=ravel_pytree(pn_isp)[0].numpy())
+
+        def f_isp_ps(params_norm):      # both options together
+            return run_pe.nll(m["T"], True, True, filter_predict, filter_correct, solver, ode,
+                              ob.build_initial_value, cov_update_fn, params_norm, copy.copy(st), x0_raw,
+                              m["H"], m["ys"], flags, ymap, lo, hi, opt, idx, ob.params)
+
+        val4, g4 = jax.value_and_grad(f_isp_ps)(pn_isp)
+        out.update(nll_fn_isp_ps=np.array(float(val4)), grad_norm_isp_ps=ravel_pytree(g4)[0].numpy())
     return out
 
 

@@ -165,8 +165,31 @@ int emu_pf(const odeu_plan& plan, const odeu_pf_io& io) {
 template <class Ode, class Tab>
 int emu_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g);
 
+// host replay of launch_sens: the per-(parameter set, direction) body of sens.cuh
+template <class Ode, class Tab>
+int emu_sens(const odeu_plan& plan, const odeu_sens_io& s) {
+  SensArgs<Ode::NP> a;
+  a.B = s.B; a.t0 = s.t0; a.h = plan.desc.step_size; a.p_opt = s.p_opt;
+  for (int j = 0; j < ODEU_MAX_GRAD; ++j) a.idx[j] = j < s.p_opt ? s.idx[j] : -1;
+  a.x0 = s.x0; a.x0_tan = s.x0_tangent; a.theta = s.theta; a.w = s.w; a.w_tan = s.w_tangent;
+  for (int k = 0; k < Ode::NP; ++k) a.theta_shared[k] = s.theta_shared ? s.theta_shared[k] : plan.theta_default[k];
+  for (int j = 0; j < (s.w_tangent ? s.p_opt : 1); ++j)
+    for (long long b = 0; b < s.B; ++b) param_sens_unit<Ode, Tab>(a, b, j);
+  return 0;
+}
+
 template <class Ode>
-int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p, const odeu_grad_io* g = nullptr) {
+int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p, const odeu_grad_io* g = nullptr,
+               const odeu_sens_io* s = nullptr) {
+  if (s) {
+    switch (plan.desc.solver_id) {
+      case ODEU_SOLVER_RKF45: return emu_sens<Ode, TabRKF45>(plan, *s);
+      case ODEU_SOLVER_DOPRI65: return emu_sens<Ode, TabDopri65>(plan, *s);
+      case ODEU_SOLVER_BS32: return emu_sens<Ode, TabBS32>(plan, *s);
+      case ODEU_SOLVER_HEUN_EULER: return emu_sens<Ode, TabHeunEuler>(plan, *s);
+    }
+    return -2;
+  }
   if (g) {
     switch (plan.desc.solver_id) {
       case ODEU_SOLVER_RKF45: return emu_grad<Ode, TabRKF45>(plan, *e, *g);
@@ -186,24 +209,25 @@ int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p,
 }
 
 static int emu_dispatch(const odeu_plan_desc& d, const double* theta_default, int p,
-                        const odeu_ekf_io* e, const odeu_pf_io* pf, const odeu_grad_io* g = nullptr) {
+                        const odeu_ekf_io* e, const odeu_pf_io* pf, const odeu_grad_io* g = nullptr,
+                        const odeu_sens_io* s = nullptr) {
   odeu_plan plan;
   plan.desc = d;
   plan.theta_default.assign(theta_default, theta_default + p);
   switch (d.ode_id) {
-    case ODEU_ODE_LORENZ: return emu_solver<OdeLorenz>(plan, e, pf, g);
-    case ODEU_ODE_VAN_DER_POL: return emu_solver<OdeVanDerPol>(plan, e, pf, g);
-    case ODEU_ODE_LOTKA_VOLTERRA: return emu_solver<OdeLotkaVolterra>(plan, e, pf, g);
-    case ODEU_ODE_PENDULUM: return emu_solver<OdePendulum>(plan, e, pf, g);
-    case ODEU_ODE_LCAO: if (d.ode_variant == 2) return emu_solver<OdeLCAO<2>>(plan, e, pf, g); break;
+    case ODEU_ODE_LORENZ: return emu_solver<OdeLorenz>(plan, e, pf, g, s);
+    case ODEU_ODE_VAN_DER_POL: return emu_solver<OdeVanDerPol>(plan, e, pf, g, s);
+    case ODEU_ODE_LOTKA_VOLTERRA: return emu_solver<OdeLotkaVolterra>(plan, e, pf, g, s);
+    case ODEU_ODE_PENDULUM: return emu_solver<OdePendulum>(plan, e, pf, g, s);
+    case ODEU_ODE_LCAO: if (d.ode_variant == 2) return emu_solver<OdeLCAO<2>>(plan, e, pf, g, s); break;
     case ODEU_ODE_HODGKIN_HUXLEY:
-      if (d.ode_variant == 0) return emu_solver<OdeHodgkinHuxley<0>>(plan, e, pf, g);
-      if (d.ode_variant == 1) return emu_solver<OdeHodgkinHuxley<1>>(plan, e, pf, g);
-      if (d.ode_variant == 4) return emu_solver<OdeHodgkinHuxley<4>>(plan, e, pf, g);
+      if (d.ode_variant == 0) return emu_solver<OdeHodgkinHuxley<0>>(plan, e, pf, g, s);
+      if (d.ode_variant == 1) return emu_solver<OdeHodgkinHuxley<1>>(plan, e, pf, g, s);
+      if (d.ode_variant == 4) return emu_solver<OdeHodgkinHuxley<4>>(plan, e, pf, g, s);
       break;
     case ODEU_ODE_MULTI_HH:
-      if (d.num_compartments == 2 && d.ode_variant == 1) return emu_solver<OdeMultiHH<1, 2>>(plan, e, pf, g);
-      if (d.num_compartments == 2 && d.ode_variant == 4) return emu_solver<OdeMultiHH<4, 2>>(plan, e, pf, g);
+      if (d.num_compartments == 2 && d.ode_variant == 1) return emu_solver<OdeMultiHH<1, 2>>(plan, e, pf, g, s);
+      if (d.num_compartments == 2 && d.ode_variant == 4) return emu_solver<OdeMultiHH<4, 2>>(plan, e, pf, g, s);
       break;
   }
   return -2;
@@ -229,6 +253,9 @@ int emu_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g
 }  // namespace odeu
 
 extern "C" {
+int hostemu_sens_run(const odeu_plan_desc* d, const double* theta_default, int p, const odeu_sens_io* s) {
+  return odeu::emu_dispatch(*d, theta_default, p, nullptr, nullptr, nullptr, s);
+}
 int hostemu_grad_run(const odeu_plan_desc* d, const double* theta_default, int p, const odeu_ekf_io* io,
                      const odeu_grad_io* g) {
   return odeu::emu_dispatch(*d, theta_default, p, io, nullptr, g);

@@ -123,3 +123,65 @@ def test_initial_state_parametrized_gradient_matches_reference(name):
 @pytest.mark.parametrize("name", ISP)
 def test_cuda_initial_state_parametrized_gradient(name):
     _check_isp("gpu", name, batch=5)
+
+
+# ---- parameter_sensitivity (scripts/run_parameter_estimation.py:750-769): Q_sqrt = diag(w(theta))
+def _check_ps(backend, name, batch=1, isp=False):
+    """Against the reference's own nll(..., parameter_sensitivity=True) and its reverse-mode gradient
+    (fixture keys *_ps / *_isp_ps), at a point off the defaults."""
+    ref = dict(np.load(os.path.join(cases.GOLDEN, f"ref_{name}.npz")))
+    sfx = "_isp_ps" if isp else "_ps"
+    if "grad_norm" + sfx not in ref:
+        pytest.skip("fixture without the parameter_sensitivity gradient")
+    spec = cases.CASES[name]
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    ob = REF_GRAD[name]()
+    keys_s, sizes, perm = runners.param_layout(ob)
+    pn = ref["pn_isp"] if isp else ref["pn_ps"]
+    theta_sorted = pn * (ref["hi"] - ref["lo"]) + ref["lo"]
+    idx_builder = np.array([int(np.nonzero(perm == j)[0][0]) for j in range(perm.size)])
+    tan = None
+    if isp:
+        x0_raw = np.full((1, 2 if name.startswith("c3") else 1), -70.0)
+        xb, tan = runners.initial_value_and_tangent(ob, x0_raw, np.repeat(theta_sorted[None], batch, 0),
+                                                    np.arange(theta_sorted.size))
+    else:
+        xb = np.repeat(m["x0"].reshape(1, -1).numpy(), batch, 0)
+    w, wt = U.run_sens(backend, plan, xb, idx_builder, t0=m["t0"], theta_shared=theta_sorted[perm], x0_tangent=tan)
+    n = xb.shape[1]
+    np.testing.assert_allclose(np.linalg.norm(w, axis=1), np.sqrt(n), rtol=1e-12)
+    assert (w >= 0).all()
+    nll, g = U.run_grad(backend, plan, xb, m["T"], idx_builder, t0=m["t0"], P0_sqrt=m["P0s"].numpy(),
+                        theta_shared=theta_sorted[perm], Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5,
+                        H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy(), correct_flags=m["flags"],
+                        xy_index_map=m["ymap"], x0_tangent=tan, Q_sqrt_diag=w, Q_sqrt_diag_tangent=wt)
+    want = float(ref["nll_fn" + sfx])
+    assert abs(nll[batch - 1] - want) <= 1e-9 * abs(want)
+    g_norm = g[batch - 1] * (ref["hi"] - ref["lo"])
+    scale = np.max(np.abs(ref["grad_norm" + sfx]))
+    np.testing.assert_allclose(g_norm, ref["grad_norm" + sfx], rtol=1e-6, atol=1e-6 * scale)
+    # the weights change the loss (they replace the configured Q_sqrt) and their tangent matters
+    assert np.abs(wt).max() > 0
+
+
+@pytest.mark.parametrize("name", list(REF_GRAD))
+def test_parameter_sensitivity_gradient_matches_reference(name):
+    _check_ps("hostemu", name)
+
+
+@pytest.mark.parametrize("name", ISP)
+def test_parameter_sensitivity_with_initial_state_parametrized(name):
+    _check_ps("hostemu", name, isp=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(REF_GRAD))
+def test_cuda_parameter_sensitivity_gradient(name):
+    _check_ps("gpu", name, batch=5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ISP)
+def test_cuda_parameter_sensitivity_with_initial_state_parametrized(name):
+    _check_ps("gpu", name, batch=3, isp=True)

@@ -46,6 +46,8 @@ def hostemu():
                                         C.POINTER(N.PfIO)]
         _emu.hostemu_grad_run.argtypes = [C.POINTER(N.PlanDesc), C.POINTER(C.c_double), C.c_int,
                                           C.POINTER(N.EkfIO), C.POINTER(N.GradIO)]
+        _emu.hostemu_sens_run.argtypes = [C.POINTER(N.PlanDesc), C.POINTER(C.c_double), C.c_int,
+                                          C.POINTER(N.SensIO)]
         _emu.hostemu_last_error.restype = C.c_char_p
     return _emu
 
@@ -225,9 +227,10 @@ def rel_err(a, b, floor=0.0):
 
 def run_grad(backend, plan, x0, T, grad_idx, *, t0=0.0, P0_sqrt=None, theta=None, theta_shared=None,
              Q_sqrt=None, gamma_sqrt=0.0, H=None, R_sqrt=None, ys=None, correct_flags=None,
-             xy_index_map=None, x0_tangent=None):
+             xy_index_map=None, x0_tangent=None, Q_sqrt_diag=None, Q_sqrt_diag_tangent=None):
     """Returns (nll [B], grad [B, p_opt]) from the product path (gpu) or the host-compiled source.
-    x0_tangent [B, p_opt, n]: d x0 / d theta_j (initial_state_parametrized)."""
+    x0_tangent [B, p_opt, n]: d x0 / d theta_j (initial_state_parametrized).
+    Q_sqrt_diag [B, n], Q_sqrt_diag_tangent [B, p_opt, n]: parameter_sensitivity weights."""
     x0 = _np(x0)
     B, n = x0.shape
     if backend == "gpu":
@@ -237,7 +240,8 @@ def run_grad(backend, plan, x0, T, grad_idx, *, t0=0.0, P0_sqrt=None, theta=None
         nll, g = ekf_grad_run(plan, tt(x0), T, grad_idx, t0=t0, P0_sqrt=P0_sqrt, theta=tt(theta),
                               theta_shared=theta_shared, Q_sqrt=Q_sqrt, gamma_sqrt=gamma_sqrt, H=H,
                               R_sqrt=R_sqrt, ys=tt(ys), correct_flags=tt(correct_flags, torch.uint8),
-                              xy_index_map=tt(xy_index_map, torch.int64), x0_tangent=tt(x0_tangent))
+                              xy_index_map=tt(xy_index_map, torch.int64), x0_tangent=tt(x0_tangent),
+                              Q_sqrt_diag=tt(Q_sqrt_diag), Q_sqrt_diag_tangent=tt(Q_sqrt_diag_tangent))
         torch.cuda.synchronize()
         return nll.cpu().numpy(), g.cpu().numpy()
     emu = hostemu()
@@ -275,8 +279,51 @@ def run_grad(backend, plan, x0, T, grad_idx, *, t0=0.0, P0_sqrt=None, theta=None
     g.p_opt, g.idx, g.grad = int(idx.size), _p(idx), _p(grad)
     if x0_tangent is not None:
         g.x0_tangent = _p(K(np.ascontiguousarray(_np(x0_tangent).transpose(1, 2, 0))))     # [p_opt][n][B]
+    if Q_sqrt_diag is not None:
+        io.Q_sqrt_diag_batch = _p(K(np.ascontiguousarray(_np(Q_sqrt_diag).T)))                 # [n][B]
+        if Q_sqrt_diag_tangent is not None:
+            g.Q_sqrt_diag_tangent = _p(K(np.ascontiguousarray(_np(Q_sqrt_diag_tangent).transpose(1, 2, 0))))
     th = (C.c_double * plan.p)(*plan.default_params)
     rc = emu.hostemu_grad_run(C.byref(plan.desc), th, plan.p, C.byref(io), C.byref(g))
     if rc != 0:
         raise ValueError(f"hostemu: {emu.hostemu_last_error().decode()} ({rc})")
     return nll, grad.T.copy()
+
+
+def run_sens(backend, plan, x0, grad_idx, *, t0=0.0, theta=None, theta_shared=None, x0_tangent=None):
+    """parameter_sensitivity weights: (w [B, n], d w / d theta_j [B, p_opt, n]) from the product path
+    (gpu, odeu_param_sensitivity) or the host-compiled source of the same kernel body."""
+    x0 = _np(x0)
+    B, n = x0.shape
+    if backend == "gpu":
+        from ode_uncertainty_b200.engine import param_sensitivity
+        dev = torch.device("cuda:0")
+        tt = lambda a: None if a is None else torch.as_tensor(np.asarray(a), dtype=torch.float64).to(dev)
+        w, wt = param_sensitivity(plan, tt(x0), grad_idx, t0=t0, theta=tt(theta), theta_shared=theta_shared,
+                                  x0_tangent=tt(x0_tangent))
+        torch.cuda.synchronize()
+        return w.cpu().numpy(), wt.cpu().numpy()
+    emu = hostemu()
+    keep = []
+
+    def K(a):
+        keep.append(a)
+        return a
+
+    idx = K(np.ascontiguousarray(np.asarray(grad_idx, dtype=np.int32)))
+    w, wt = np.zeros((n, B)), np.zeros((idx.size, n, B))
+    s = N.SensIO()
+    s.B, s.t0, s.x0 = B, float(t0), _p(K(np.ascontiguousarray(x0.T)))
+    if theta is not None:
+        s.theta = _p(K(np.ascontiguousarray(_np(theta).T)))
+    if theta_shared is not None:
+        s.theta_shared = _p(K(_np(theta_shared)))
+    s.p_opt, s.idx = int(idx.size), _p(idx)
+    if x0_tangent is not None:
+        s.x0_tangent = _p(K(np.ascontiguousarray(_np(x0_tangent).transpose(1, 2, 0))))
+    s.w, s.w_tangent = _p(w), _p(wt)
+    th = (C.c_double * plan.p)(*plan.default_params)
+    rc = emu.hostemu_sens_run(C.byref(plan.desc), th, plan.p, C.byref(s))
+    if rc != 0:
+        raise ValueError(f"hostemu: {emu.hostemu_last_error().decode()} ({rc})")
+    return w.T.copy(), wt.transpose(2, 0, 1).copy()

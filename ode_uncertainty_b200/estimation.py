@@ -86,7 +86,8 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
              num_tempering_stages: int = 10, final_gamma_zero: bool = True, obs_noise_var: float = 0.1,
              gamma_noise_schedule: NoiseSchedule = ExponentialDecaySchedule(), lbfgs_maxiter: int = 200,
              num_random_runs: int = 0, seed: int = 7, initial_state_parametrized: bool = False,
-             parameter_sensitivity: bool = False, device="cuda", verbose: bool = False) -> Dict[str, np.ndarray]:
+             parameter_sensitivity: bool = False, device="cuda", verbose: bool = False,
+             _P0_sqrt: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """scripts/run_parameter_estimation.py:49-308 with the same keyword meaning (observations
     are passed as arrays `ts_y`, `ys_x` instead of an H5 path)."""
     from scipy.optimize import minimize
@@ -102,6 +103,8 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
     n = plan.n
     x0_built = ode_builder.build_initial_value(_arr(x0), ode_builder.params).reshape(-1)
     P0_sqrt = np.eye(n) * 1e-12 if P0 is None else np.linalg.cholesky(_arr(P0))
+    if _P0_sqrt is not None:
+        P0_sqrt = _arr(_P0_sqrt).reshape(n, n)
     h = solver_builder.h
     num_steps, flags, ymap = observation_schedule(t0, tN, h, ts_y)
     H = _arr(measurement_matrix)
@@ -203,3 +206,33 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
             "params_default": default_sorted[opt_idx_sorted], "params_name": np.array(names),
             "nll_optims": nll_optims, "num_lbfgs_iters": iters, "num_nll_evals": nfev,
             "num_nll_jac_evals": nfev.copy(), "gammas": np.array(gammas), "kernel_launches": launches}
+
+
+def optimize_baseline(solver_builder, ode_builder, *, x0, ts_y, ys_x, measurement_matrix,
+                      params_range: Dict[str, Tuple[float, float]],
+                      params_optimized: Optional[Dict[str, bool]] = None, t0: float = 0.0, tN: float = 80.0,
+                      obs_noise_var: float = 0.1, lbfgs_maxiter: int = 200, num_random_runs: int = 0, seed: int = 7,
+                      initial_state_parametrized: bool = False, device="cuda",
+                      verbose: bool = False) -> Dict[str, np.ndarray]:
+    """scripts/run_parameter_estimation_baseline.py:40-262: the plain-RK least-squares baseline,
+    loss `nll` :552-632 = sum over observation steps of negative_log_gaussian_sqrt(y, H x_RK(theta), R_sqrt).
+
+    Served by the SAME gradient kernels with a degenerate filter: P0 = 0, no process noise
+    (disable_cov_update, Q = 0) keep P = 0, hence S = R, the gain is exactly zero, the state is the
+    plain RK solution and every NLL term is the baseline's ("same kernel, different
+    reduction/branch").  One stage, no tempering; arrays come back without the stage axis like the
+    reference's datasets (:236-259)."""
+    from .filters import SQRT_EKF
+
+    n = ode_builder.build_initial_value(_arr(x0), ode_builder.params).size
+    res = optimize(SQRT_EKF(disable_cov_update=True), solver_builder, ode_builder, x0=x0, ts_y=ts_y, ys_x=ys_x,
+                   measurement_matrix=measurement_matrix, params_range=params_range,
+                   gamma_noise_weights=np.zeros(n), params_optimized=params_optimized, t0=t0, tN=tN,
+                   num_tempering_stages=1, final_gamma_zero=True, obs_noise_var=obs_noise_var,
+                   lbfgs_maxiter=lbfgs_maxiter, num_random_runs=num_random_runs, seed=seed,
+                   initial_state_parametrized=initial_state_parametrized, device=device, verbose=verbose,
+                   _P0_sqrt=np.zeros((n, n)))
+    for k in ("params_optims", "nll_optims", "num_lbfgs_iters", "num_nll_evals", "num_nll_jac_evals"):
+        res[k] = res[k][:, 0]
+    res.pop("gammas")
+    return res

@@ -357,6 +357,17 @@ def ekf_nll(filter_builder, solver_builder, ode_builder, *, params_norm, params_
 
 
 # ------------------------------------------------------------------------------------------------
+def baseline_nll(solver_builder, ode_builder, **kw) -> torch.Tensor:
+    """Batched plain-RK least-squares loss, `nll()` of scripts/run_parameter_estimation_baseline.py:552-632,
+    with the keyword meaning of `ekf_nll` (no P0 / Q / gamma): the degenerate filter P0 = 0, Q = 0,
+    disable_cov_update has zero gain, so each term is negative_log_gaussian_sqrt(y, H x_RK, R_sqrt)."""
+    from .filters import SQRT_EKF
+
+    n = ode_builder.build_initial_value(_arr(kw["x0"]), ode_builder.params).size
+    return ekf_nll(SQRT_EKF(disable_cov_update=True), solver_builder, ode_builder, P0_sqrt=np.zeros((n, n)),
+                   Q_sqrt=np.zeros((n, n)), gamma_sqrt=0.0, **kw)
+
+
 def pf_unroll(filter_builder, solver_builder, ode_builder, *, x0, t0: float, num_steps: int, seed: int = 7,
               save_interval: int = 1, use_static_cov_fn: bool = False, particle_offset: int = 0,
               num_particles: Optional[int] = None, device="cuda") -> Dict[str, torch.Tensor]:

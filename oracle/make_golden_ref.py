@@ -194,6 +194,35 @@ def run_nll_and_grad(spec):
     return out
 
 
+def run_baseline_nll_and_grad(spec):
+    """The reference's plain-RK least-squares baseline loss (scripts/run_parameter_estimation_baseline.py
+    ::nll :552-632) and its gradient w.r.t. the normalised parameters, off the defaults."""
+    run_base = _load_script("run_parameter_estimation_baseline")
+    m = cases.materialize(spec)
+    ob, sb, _, _ = builders(spec)
+    ode = ob.build()
+    sb.setup(ode, ob.params)
+    solver = sb.build_parametrized()
+    st = sb.init_state(jnp.array(m["t0"]), m["x0"])
+    keys = list(ob.params)
+    shp = {k: ob.params[k].shape[-1:] for k in keys}
+    lo = {k: torch.minimum(0.5 * ob.params[k], 2.0 * ob.params[k]).reshape(shp[k]) for k in keys}
+    hi = {k: torch.maximum(0.5 * ob.params[k], 2.0 * ob.params[k]).reshape(shp[k]) for k in keys}
+    opt = {k: jnp.full(shp[k], True) for k in keys}
+    pn = {k: (ob.params[k].reshape(shp[k]) - lo[k]) / (hi[k] - lo[k]) + 0.05 for k in keys}
+    idx = jnp.flatnonzero(ravel_pytree(opt)[0])
+    flags = torch.as_tensor(m["flags"].astype(bool))
+    ymap = torch.as_tensor(m["ymap"])
+
+    def f(params_norm):
+        return run_base.nll(m["T"], False, solver, ode, ob.build_initial_value, params_norm, copy.copy(st),
+                            m["x0"], m["H"], m["ys"], m["Rs"], flags, ymap, lo, hi, idx, ob.params)
+
+    val, g = jax.value_and_grad(f)(pn)
+    return dict(nll_base=np.array(float(val)), grad_norm_base=ravel_pytree(g)[0].numpy(),
+                pn_base=ravel_pytree(pn)[0].numpy(), lo=ravel_pytree(lo)[0].numpy(), hi=ravel_pytree(hi)[0].numpy())
+
+
 def sync_times_fixture():
     """The reference's own sync_times (src/utils.py:181-215) on the float aranges its scripts
     build (scripts/run_filter.py:99-105) for a few observation cadences."""
@@ -229,6 +258,12 @@ if __name__ == "__main__":
     if sys.argv[1:] and sys.argv[1] == "dense":
         for name in (sys.argv[2:] or list(cases.DENSE_CASES)):
             dense_fixture(name)
+        sys.exit(0)
+    if sys.argv[1:] and sys.argv[1] == "baseline":
+        for name in (sys.argv[2:] or GRAD_CASES):
+            out = run_baseline_nll_and_grad(cases.CASES[name])
+            np.savez_compressed(os.path.join(cases.GOLDEN, f"ref_baseline_{name}.npz"), **out)
+            print(f"baseline {name}: nll={float(out['nll_base']):.12g}")
         sys.exit(0)
     names = sys.argv[1:] or list(cases.CASES)
     if not sys.argv[1:] or "sync_times" in names:

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libodeu.so")
+LIB_PATH = os.environ.get("ODEU_LIB", os.path.join(_HERE, "libodeu.so"))   # ODEU_LIB: A/B builds (dev)
 
 # enums of include/odeu.h
 ODE_LORENZ, ODE_VAN_DER_POL, ODE_LOTKA_VOLTERRA, ODE_PENDULUM, ODE_LCAO, ODE_HODGKIN_HUXLEY, ODE_MULTI_HH = range(7)

@@ -12,9 +12,12 @@ namespace odeu {
 // per-ODE launch shape: BLOCK threads, MINB resident blocks per SM (register cap), KC tangent
 // columns carried per RK pass
 template <class Ode>
+#ifndef ODEU_THREAD_MINB
+#define ODEU_THREAD_MINB 6      // 64-thread CTAs per SM for n <= 4: 6 -> up to 168 registers, no spills (measured: Lorenz 18.96 (8) / 21.26 (6) / 20.83 (5) / 20.29 (4) G trajectory-steps/s)
+#endif
 struct LaunchCfg {
   static constexpr int BLOCK = 64;
-  static constexpr int MINB = (Ode::NX <= 4) ? 8 : 2;
+  static constexpr int MINB = (Ode::NX <= 4) ? ODEU_THREAD_MINB : 2;
   static constexpr int KC = (Ode::NX <= 4) ? Ode::NX : 1;
 };
 

@@ -461,7 +461,7 @@ def main():
                        "observations": "every step, H=I, R=1e-3 I, shared sequence",
                        "units_per_step": units_per_step, "l2": "flushed (256 MB write) between timed steps",
                        "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
-            "roofline": {"bound": "fp64", "kernel": "ekf_thread_kernel<OdeLorenz,TabRKF45>",
+            "roofline": {"bound": "fp64", "kernel": "ekf_thread_sched_kernel<OdeLorenz,TabRKF45,3,3,64,6>",
                          "achieved": achieved, "peak": dfma_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / dfma_peak_tflops,
                          "peak_source": "measured in this run: odeu_bench_dfma (8 DFMA chains/thread, 148x8x256 threads)",

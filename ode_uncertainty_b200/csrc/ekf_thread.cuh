@@ -165,6 +165,16 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   }
   long long next_save = si;  // step count at which the next slot is written
   long long slot = 1;
+  // The final-state y_hat / S are those of the LAST measurement update of the run (the reference
+  // state dict simply keeps them, sqrt_ekf.py:370-372).  Publishing them at every observation step
+  // cost L + L^2 global stores per step (12 of the 12.1 stores per step at C2, +2.5 % run time), so
+  // only the step that is the last observation writes them: scan the flags backwards once (one
+  // load when every step is observed; a segment stops at its own first step).
+  long long last_obs = -1;
+  if (LK != 0 && a.has_obs && (a.yhatT || a.ST)) {
+    for (long long s = a.T - 1; s >= sg.step0; --s)
+      if (a.flags[s]) { last_obs = s; break; }
+  }
 
   for (long long step = sg.step0; step < sg.step1; ++step) {
     // ---- predict (src/filters/sqrt_ekf.py:92-197)
@@ -199,8 +209,8 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     const bool slot_ahead = si > 0 && next_save <= a.T;   // a further save point exists
     sink.y1 = (slot_ahead && a.out_yhat) ? a.out_yhat + slot * L * B + b : nullptr;
     sink.S1 = (slot_ahead && a.out_S) ? a.out_S + slot * L * L * B + b : nullptr;
-    sink.y2 = a.yhatT ? a.yhatT + b : nullptr;
-    sink.S2 = a.ST ? a.ST + b : nullptr;
+    sink.y2 = (a.yhatT && step == last_obs) ? a.yhatT + b : nullptr;
+    sink.S2 = (a.ST && step == last_obs) ? a.ST + b : nullptr;
     if constexpr (LK == -1) {
       if (a.has_obs && a.flags[step]) {
         const long long oi = a.ymap[step];

@@ -92,28 +92,54 @@ ODEU_HD void pf_particle(const PfArgs<Ode::NX, Ode::NP>& a, const long long m) {
     if (m == 0 && a.out_t) a.out_t[0] = t;
   }
   long long next_save = si, slot = 1;
+  double spare = 0.0;          // second normal of the last Box-Muller block of an even step
+  bool have_spare = false;
   for (long long step = 0; step < a.T; ++step) {
     double xn[n];
     rk_step_plain<Ode, Tab>(t, a.h, x, th, xn, eps);
     t = t + a.h;
     if (gid != 0 && !a.noise_free) {
       const unsigned long long gstep = (unsigned long long)(a.step_offset + step);
-      if (a.cov_fn == COV_OUTER) {
-        double z0, z1;
-        Philox::normal2(a.seed, gid, gstep, 0, &z0, &z1);
+      // NZ standard normals per step (one for the rank-one Outer plugin, n otherwise).  Box-Muller
+      // yields them in pairs: an odd NZ would waste one per step, so two consecutive steps
+      // (2q, 2q + 1) share the NZ blocks keyed (particle, q): the even step takes normals 0..NZ-1
+      // and keeps normal NZ for the odd step (recomputed if a run starts on an odd step), which
+      // adds normals NZ+1..2NZ-1.  Keyed by GLOBAL particle and step: sharding/resume invariant.
+      const bool outer = a.cov_fn == COV_OUTER;
+      double z[n + 1];
+      const int nz = outer ? 1 : n;
+      if (nz & 1) {
+        const unsigned long long q = gstep >> 1;
+        const int nb = (nz + 1) / 2;                    // blocks of the even step
+        if (!(gstep & 1)) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) xn[i] = fma(a.cov_scale * eps[i], z0, xn[i]);
+          for (int i = 0; i < (n + 1) / 2; ++i)
+            if (i < nb) Philox::normal2(a.seed, gid, q, (unsigned)i, &z[2 * i], &z[2 * i + 1]);
+          spare = z[nz];
+          have_spare = true;
+        } else {
+          if (!have_spare) {
+            double dummy;
+            Philox::normal2(a.seed, gid, q, (unsigned)(nb - 1), &dummy, &spare);
+          }
+          z[0] = spare;
+          have_spare = false;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i)
+            if (i < nz / 2) Philox::normal2(a.seed, gid, q, (unsigned)(nb + i), &z[1 + 2 * i], &z[2 + 2 * i]);
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < n; i += 2) {
-          double z0, z1;
-          Philox::normal2(a.seed, gid, gstep, (unsigned)(i / 2), &z0, &z1);
+        for (int i = 0; i < n / 2; ++i) Philox::normal2(a.seed, gid, gstep, (unsigned)i, &z[2 * i], &z[2 * i + 1]);
+      }
+      if (outer) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) xn[i] = fma(a.cov_scale * eps[i], z[0], xn[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
           const double s0 = (a.cov_fn == COV_DIAGONAL) ? a.cov_scale * eps[i] : a.cov_scale;
-          xn[i] = fma(s0, z0, xn[i]);
-          if (i + 1 < n) {
-            const double s1 = (a.cov_fn == COV_DIAGONAL) ? a.cov_scale * eps[i + 1] : a.cov_scale;
-            xn[i + 1] = fma(s1, z1, xn[i + 1]);
-          }
+          xn[i] = fma(s0, z[i], xn[i]);
         }
       }
     }

@@ -268,14 +268,12 @@ def initial_value_and_tangent(ode_builder, x0_raw, flat_sorted: np.ndarray, opt_
 
 def solve_trajectory(plan: Plan, x0, num_steps: int, *, t0: float = 0.0, theta_shared=None, device="cuda") -> np.ndarray:
     """Plain fixed-step solution x(t0), x(t0 + h), ... [num_steps + 1, n] of ONE initial value with the
-    plan's solver (what scripts/run_ode_solver.py:56-74 produces as ground truth): the predict-only
-    filter with a negligible initial covariance, every step saved.  Used to synthesise observation
-    sequences on the product path (bench.py, tools/)."""
-    dev = torch.device(device)
+    plan's solver (what scripts/run_ode_solver.py:56-74 produces as ground truth): the noise-free
+    particle of the ensemble kernel (a plain RK step, no tangents), every step saved.  Used to
+    synthesise observation sequences on the product path (bench.py, tools/)."""
     n = plan.n
-    r = ekf_run(plan, torch.as_tensor(_arr(x0).reshape(1, n)).to(dev), int(num_steps), t0=float(t0),
-                P0_sqrt=np.eye(n) * 1e-12, theta_shared=theta_shared, save_interval=1, save_keys=("x",),
-                want_final=False)
+    r = pf_run(plan, 1, int(num_steps), x0_shared=_arr(x0).reshape(n), t0=float(t0), theta_shared=theta_shared,
+               save_interval=1, device=device, noise_free=True)
     return r.traj["x"][:, 0, :].cpu().numpy()
 
 

@@ -155,3 +155,20 @@ def test_particle_filter_unroll_shapes_and_particle_zero():
     xs, _ = RC.rk_run("Lorenz", "RKF45", 0.01, [1.0, 1.0, 1.0], 50, theta=[10.0, 8.0 / 3, 28.0])
     np.testing.assert_allclose(tr["x"][:, 0, 0], xs[::5], rtol=1e-12)
     assert np.abs(tr["x"][-1, 1:] - tr["x"][-1, 0]).max() > 0
+
+
+def test_solve_trajectory_equals_predict_only_filter_mean():
+    """runners.solve_trajectory (plain RK steps of the ensemble kernel, scripts/run_ode_solver.py:56-74)
+    gives the same solution as the mean of the prediction-only filter."""
+    import numpy as np
+    import torch
+    from ode_uncertainty_b200 import Plan, _native as N, ekf_run, runners
+    for ode_id, kw, x0 in ((N.ODE_LORENZ, {}, [1.0, 1.0, 1.0]),
+                           (N.ODE_HODGKIN_HUXLEY, dict(ode_variant=1), [-70.0, 0.01, 0.99, 0.01, 0.03, 0.0, 0.4])):
+        plan = Plan(ode_id=ode_id, solver_id=N.SOLVER_RKF45, step_size=0.01, **kw)
+        xs = runners.solve_trajectory(plan, x0, 300)
+        r = ekf_run(plan, torch.tensor([x0], dtype=torch.float64, device="cuda"), 300, P0_sqrt=np.eye(plan.n) * 1e-12,
+                    save_interval=1, save_keys=("x",), want_final=False)
+        ref = r.traj["x"][:, 0, :].cpu().numpy()
+        assert xs.shape == ref.shape == (301, plan.n)
+        np.testing.assert_allclose(xs, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())

@@ -19,7 +19,7 @@ for system, ode_id in (("Lorenz", N.ODE_LORENZ), ("VanDerPol", N.ODE_VAN_DER_POL
             ts = []
             for _ in range(4):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); ekf_run(plan, x0, T, dynamic=dyn, **k); e1.record(); torch.cuda.synchronize()
+                e0.record(); ekf_run(plan, x0, T, dynamic=dyn, want_final=not os.environ.get('SWEEP_NOFINAL'), **k); e1.record(); torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             res[(system, tag, dyn)] = B * T / (min(ts[1:]) * 1e-3) / 1e9
 print(os.environ.get("ODEU_SCHED_NSEG"), os.environ.get("ODEU_SCHED_CAP"),

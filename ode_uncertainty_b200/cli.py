@@ -9,6 +9,7 @@ the runner that mirrors the script's `main()`:
 
     python -m ode_uncertainty_b200.cli run_filter            --config cfg.yaml [--key value ...]
     python -m ode_uncertainty_b200.cli run_parameter_estimation optimize --config cfg.yaml
+    python -m ode_uncertainty_b200.cli run_parameter_estimation_baseline optimize --config cfg.yaml
     python -m ode_uncertainty_b200.cli run_calibration       --config cfg.yaml
 
 Differences to the reference CLI: results are written as `.npz` with the reference's dataset names
@@ -87,7 +88,8 @@ def _load_observations(cfg: Dict[str, Any]) -> None:
 def main(argv=None) -> Dict[str, np.ndarray]:
     ap = argparse.ArgumentParser(prog="ode_uncertainty_b200.cli", description=__doc__,
                                  formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("script", choices=["run_filter", "run_parameter_estimation", "run_calibration"])
+    ap.add_argument("script", choices=["run_filter", "run_parameter_estimation", "run_parameter_estimation_baseline",
+                                       "run_calibration"])
     ap.add_argument("subcommand", nargs="?", default=None, help="optimize (run_parameter_estimation)")
     ap.add_argument("--config", required=True)
     args, rest = ap.parse_known_args(argv)
@@ -95,7 +97,7 @@ def main(argv=None) -> Dict[str, np.ndarray]:
         ap.error("overrides must be given as --key value pairs")
     overrides = {k[2:]: v for k, v in zip(rest[0::2], rest[1::2])}
     cfg = load_config(args.config, overrides)
-    if args.script != "run_parameter_estimation":
+    if not args.script.startswith("run_parameter_estimation"):
         cfg.pop("initial_state_parametrized", None)
         cfg.pop("parameter_sensitivity", None)
     if isinstance(cfg.get("output"), str):
@@ -109,6 +111,12 @@ def main(argv=None) -> Dict[str, np.ndarray]:
         ap.error("only the `optimize` subcommand of run_parameter_estimation is served")
     output = cfg.pop("output", None)
     _load_observations(cfg)
+    if args.script == "run_parameter_estimation_baseline":   # scripts/run_parameter_estimation_baseline.py:40-262
+        res = estimation.optimize_baseline(cfg.pop("solver_builder"), cfg.pop("ode_builder"), **cfg)
+        if output is not None:
+            os.makedirs(os.path.dirname(os.path.abspath(output)), exist_ok=True)
+            np.savez(output, **res)
+        return res
     res = estimation.optimize(cfg.pop("filter_builder"), cfg.pop("solver_builder"), cfg.pop("ode_builder"), **cfg)
     if output is not None:
         os.makedirs(os.path.dirname(os.path.abspath(output)), exist_ok=True)

@@ -1,7 +1,7 @@
 """Developer scratch check: host-compiled kernel source vs the torch oracle (not a test)."""
 import sys, time, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))  # lives under tests/: it imports the oracle
 import numpy as np, torch
 from oracle import ref_torch as R
 import util as U

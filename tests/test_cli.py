@@ -102,3 +102,55 @@ def test_run_filter_from_yaml_equals_direct_call(tmp_path):
     np.testing.assert_array_equal(res["P"], ref["P"])
     saved = np.load(str(out)[:-3] + ".npz")
     assert saved["x"].shape == (101, 1, 1, 3) and set(["t", "x", "eps", "P_sqrt"]).issubset(saved.files)
+
+
+@pytest.mark.gpu
+def test_baseline_parameter_estimation_from_yaml(tmp_path):
+    """configs/params_baseline/*.yaml shape (scripts/run_parameter_estimation_baseline.py:40-262) with an
+    embedded RK solver: observations from an .npz `y_path`, results with the reference's dataset names."""
+    from ode_uncertainty_b200 import Plan, _native as N, runners
+    truth, h, T = np.array([1.5, 1.0, 3.0, 1.0]), 0.01, 300
+    xs = runners.solve_trajectory(Plan(N.ODE_LOTKA_VOLTERRA, N.SOLVER_RKF45, h), [1.0, 1.0], T, theta_shared=truth)
+    yp = tmp_path / "obs.npz"
+    np.savez(yp, t=h * np.arange(1, T + 1), x=xs[1:] + np.random.default_rng(2).normal(0, 0.05, (T, 2)))
+    out = tmp_path / "res" / "lv.h5"
+    p = tmp_path / "base.yaml"
+    p.write_text(f"""
+output: {out}
+solver_builder:
+  class_path: src.solvers.RKF45
+  init_args:
+    step_size: {h}
+ode_builder:
+  class_path: src.ode.LotkaVolterra
+x0: '[[1.0, 1.0]]'
+t0: 0.0
+tN: {T * h}
+y_path: {yp}
+measurement_matrix: '[[1, 0], [0, 1]]'
+params_range:
+  alpha: [0.5, 3.0]
+  beta: [0.3, 2.0]
+  gamma: [1.0, 5.0]
+  delta: [0.3, 2.0]
+params_optimized:
+  alpha: true
+  beta: true
+  gamma: false
+  delta: true
+obs_noise_var: 0.0025
+initial_state_parametrized: false
+lbfgs_maxiter: 80
+num_random_runs: 3
+seed: 621
+num_processes: 4
+disable_pbar: true
+verbose: false
+""")
+    res = cli.main(["run_parameter_estimation_baseline", "optimize", "--config", str(p)])
+    assert res["params_optims"].shape == (3, 3) and list(res["params_name"]) == ["alpha", "beta", "delta"]
+    best = int(np.argmin(res["nll_optims"]))
+    np.testing.assert_allclose(res["params_optims"][best], [1.5, 1.0, 1.0], rtol=0.05)
+    saved = np.load(str(out)[:-3] + ".npz")
+    assert set(["params_inits", "params_optims", "params_default", "params_name", "nll_optims", "num_lbfgs_iters",
+                "num_nll_evals", "num_nll_jac_evals"]).issubset(saved.files)

@@ -313,31 +313,46 @@ def main():
         best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3))
     dfma_peak_tflops = best / 1e12
 
-    # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
-        res = step_resident()
+    def run_steps(k):
+        """k steps enqueued back to back (launches are asynchronous on the stream, as a production
+        caller issues them), each bracketed by its own events and preceded by the L2 flush; ONE
+        synchronize at the end, so a host-side stall cannot idle the GPU inside the region."""
+        evs, last = [], None
+        for _ in range(k):
+            flush.fill_(1.0)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            r_l = one("Lorenz", inp["Lorenz"]["x0_dev"], inp["Lorenz"]["ys_dev"])
+            ev[1].record()
+            r_v = one("VanDerPol", inp["VanDerPol"]["x0_dev"], inp["VanDerPol"]["ys_dev"])
+            ev[2].record()
+            evs.append(ev)
+            last = (r_l, r_v)
+        torch.cuda.synchronize()
+        return evs, last
+
+    # ---- warm-up: the SAME loop as the timed region (flush kernel, events, allocator state).  The
+    # clock sampler starts BEFORE it (its start-up sleeps 0.3 s; an idle gap right before the timed
+    # region lets the GPU drop to idle clocks), so its samples cover warm-up + timed region.
+    sampler = ClockSampler(local_rank)
+    if not os.environ.get("ODEU_BENCH_NO_SAMPLER"):      # A/B knob: is a slow launch caused by the nvidia-smi poll?
+        sampler.start()
+    run_steps(max(args.warmup, 3))
     barrier()
 
     # ---- timed region (device-resident inputs): K steps, L2 flushed between steps
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = launch_count()
     step_ms, lorenz_ms, vdp_ms = [], [], []
     barrier()
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1.0)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        ev[0].record()
-        r_l = one("Lorenz", inp["Lorenz"]["x0_dev"], inp["Lorenz"]["ys_dev"])
-        ev[1].record()
-        r_v = one("VanDerPol", inp["VanDerPol"]["x0_dev"], inp["VanDerPol"]["ys_dev"])
-        ev[2].record()
-        torch.cuda.synchronize()
+    evs, (r_l, r_v) = run_steps(args.steps)
+    for ev in evs:
         lorenz_ms.append(ev[0].elapsed_time(ev[1]))
         vdp_ms.append(ev[1].elapsed_time(ev[2]))
         step_ms.append(ev[0].elapsed_time(ev[2]))
     barrier()
+    if os.environ.get("ODEU_BENCH_TRACE") and rank == 0:
+        print("per-step ms (lorenz, vdp):", [(round(a_, 2), round(b_, 2)) for a_, b_ in zip(lorenz_ms, vdp_ms)], file=sys.stderr)
     wall = time.perf_counter() - wall0
     launches = launch_count() - launches0
     clocks = sampler.stop()

@@ -128,12 +128,30 @@ def test_time_segmented_run_is_bitwise_identical(name):
                   xy_index_map=m["ymap"])
     whole = U.run_ekf("hostemu", plan, x0, m["T"], **kw)
     seg = U.run_ekf("hostemu", plan, x0, m["T"], segmented=True, **kw)
-    for k in ("xT", "PT", "epsT"):
+    for k in ("xT", "PT", "epsT", "yhatT", "ST"):
         np.testing.assert_array_equal(seg[k], whole[k])
     # the log-determinant part of the NLL is accumulated as a pivot product per segment
     # (LogProd, ekf_core.cuh), so segmenting changes its rounding, not the state
     np.testing.assert_allclose(seg["nll"], whole["nll"], rtol=1e-12, atol=1e-12)
     assert seg["tT"] == whole["tT"]
+    if m["L"] > 0:
+        # the final-state y_hat / S come from the LAST observation step, which only that step writes
+        # (ekf_thread.cuh): observations every third step that stop after 60 % of the run - the last
+        # one lies in an earlier time segment than the end of the run
+        T = m["T"]
+        flags = np.zeros(T, np.uint8)
+        flags[2:int(0.6 * T):3] = 1
+        last = int(np.nonzero(flags)[0][-1])
+        kw2 = dict(kw, correct_flags=flags, xy_index_map=np.minimum(np.arange(T), m["ys"].shape[0] - 1))
+        whole = U.run_ekf("hostemu", plan, x0, T, **kw2)
+        seg = U.run_ekf("hostemu", plan, x0, T, segmented=True, **kw2)
+        upto = U.run_ekf("hostemu", plan, x0, last + 1, **{**kw2, "correct_flags": flags[:last + 1],
+                                                            "xy_index_map": kw2["xy_index_map"][:last + 1]})
+        for k in ("xT", "PT", "yhatT", "ST"):
+            np.testing.assert_array_equal(seg[k], whole[k])
+        assert np.abs(whole["ST"]).max() > 0
+        np.testing.assert_array_equal(whole["yhatT"], upto["yhatT"])      # = those of the run cut at the last observation
+        np.testing.assert_array_equal(whole["ST"], upto["ST"])
 
 
 @pytest.mark.parametrize("name", ["hh_r1_rkf45_temper", "hh_full_rkf45_small_h", "c3_mhh_r1_rkf45_temper"])

@@ -135,6 +135,16 @@ def test_dynamic_scheduler_equals_static_launch_bitwise():
             assert torch.equal(getattr(a, k), getattr(b, k)), k
         assert torch.allclose(a.nll, b.nll, rtol=1e-12, atol=1e-12)
         assert float(a.tT) == float(b.tT)
+        # observations every third step that stop after 60 % of the run: the final y_hat / S come from
+        # a step in an EARLIER time segment than the end of the run (only that step writes them)
+        fl = torch.zeros(T, dtype=torch.uint8, device=dev)
+        fl[2:int(0.6 * T):3] = 1
+        kw2 = dict(kw, correct_flags=fl)
+        a = ekf_run(plan, x0, T, dynamic=True, **kw2)
+        b = ekf_run(plan, x0, T, dynamic=False, **kw2)
+        for k in ("xT", "PT", "yhatT", "ST"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+        assert float(a.ST.abs().max()) > 0
         # prediction only as well
         a = ekf_run(plan, x0, T, dynamic=True)
         b = ekf_run(plan, x0, T, dynamic=False)

@@ -240,6 +240,8 @@ struct ObsSink {
   double* y1; double* S1;   // upcoming trajectory slot (nullable)
   double* y2; double* S2;   // final-state outputs (nullable)
   long long stride;
+  bool any;                 // some pointer is set (warp-uniform): lets the caller branch around the
+                            // whole publication instead of issuing 2 (L + L^2) predicated-off stores
   ODEU_HD void put_y(int l, double v) const {
     if (y1) y1[l * stride] = v;
     if (y2) y2[l * stride] = v;
@@ -465,17 +467,26 @@ template <int n, int L>
 ODEU_HD double correct_step_lead(const double* R, const double* y, double* x, double (*P)[n],
                                  const ObsSink& sink, LogProd* lp = nullptr) {
   double d[L], Ls[L][L], inv[L], Smat[L][L];
+  // publication of the pre-update y_hat / S: rare on throughput runs (only the last observation step
+  // of a run writes the final-state buffers), so it sits behind ONE uniform branch - as predicated
+  // stores it cost ~100 of the ~1,000 instructions of a Lorenz step (ncu source view, round 1g)
+  if (sink.any) {
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      sink.put_y(l, x[l]);
+#pragma unroll
+      for (int m = 0; m <= l; ++m) {
+        const double s = P[l][m] + R[l * L + m];
+        sink.put_S(l * L + m, s);
+        if (m != l) sink.put_S(m * L + l, s);
+      }
+    }
+  }
 #pragma unroll
   for (int l = 0; l < L; ++l) {
-    sink.put_y(l, x[l]);
     d[l] = y[l] - x[l];
 #pragma unroll
-    for (int m = 0; m <= l; ++m) {
-      const double s = P[l][m] + R[l * L + m];
-      Smat[l][m] = s;
-      sink.put_S(l * L + m, s);
-      if (m != l) sink.put_S(m * L + l, s);
-    }
+    for (int m = 0; m <= l; ++m) Smat[l][m] = P[l][m] + R[l * L + m];
   }
   bool all_tiny = true;
   double piv = 1.0;

@@ -206,11 +206,16 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     // ---- correct + log-likelihood (src/filters/sqrt_ekf.py:337-376, src/utils.py:109-128)
     ObsSink sink;
     sink.stride = B;
-    const bool slot_ahead = si > 0 && next_save <= a.T;   // a further save point exists
-    sink.y1 = (slot_ahead && a.out_yhat) ? a.out_yhat + slot * L * B + b : nullptr;
-    sink.S1 = (slot_ahead && a.out_S) ? a.out_S + slot * L * L * B + b : nullptr;
-    sink.y2 = (a.yhatT && step == last_obs) ? a.yhatT + b : nullptr;
-    sink.S2 = (a.ST && step == last_obs) ? a.ST + b : nullptr;
+    sink.y1 = sink.S1 = sink.y2 = sink.S2 = nullptr;
+    if (si > 0 && next_save <= a.T) {                      // a further save point exists
+      if (a.out_yhat) sink.y1 = a.out_yhat + slot * L * B + b;
+      if (a.out_S) sink.S1 = a.out_S + slot * L * L * B + b;
+    }
+    if (step == last_obs) {
+      if (a.yhatT) sink.y2 = a.yhatT + b;
+      if (a.ST) sink.S2 = a.ST + b;
+    }
+    sink.any = sink.y1 || sink.S1 || sink.y2 || sink.S2;
     if constexpr (LK == -1) {
       if (a.has_obs && a.flags[step]) {
         const long long oi = a.ymap[step];
@@ -224,10 +229,11 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     } else if constexpr (LK > 0) {
       if (a.flags[step]) {
         const long long oi = a.ymap[step];
+        const double* yp = a.ys_per_traj ? a.ys + oi * LK * B + b : a.ys + oi * LK;   // one address, one stride
+        const long long ystr = a.ys_per_traj ? B : 1;
         double y[LK];
 #pragma unroll
-        for (int l = 0; l < LK; ++l)
-          y[l] = a.ys_per_traj ? a.ys[(oi * LK + l) * B + b] : a.ys[oi * LK + l];
+        for (int l = 0; l < LK; ++l) y[l] = yp[l * ystr];
         nll += nll_term(correct_step_lead<n, LK>(a.R, y, x, P, sink, a.nan_to_num ? nullptr : &lp), a.nan_to_num);
         obs_fresh = true;
       }

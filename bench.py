@@ -207,18 +207,18 @@ def _other_configs(dev, timed):
               H=H, R_sqrt=np.eye(2) * 0.1 ** 0.5, ys=torch.from_numpy(ys).to(dev),
               correct_flags=torch.ones(T3, dtype=torch.uint8, device=dev), xy_index_map=torch.arange(T3, device=dev))
     x0b = torch.from_numpy(np.repeat(x0[None, :], B3, 0)).to(dev)
-    t_nll = timed(lambda: ekf_run(plan, x0b, T3, want_final=False, minimal=True, **kw), reps=1)
+    t_nll = timed(lambda: ekf_run(plan, x0b, T3, want_final=False, minimal=True, **kw), reps=2)
     out["c3_hh_loss"] = {"param_set_steps_per_s": B3 * T3 / t_nll, "sample": f"B={B3} x T={T3} (config: T=10000), n=14, L=2",
                          "alg_tflops": B3 * T3 / t_nll * 40.7e3 / 1e12}
     T3g = 200
     kwg = dict(kw, ys=kw["ys"][:T3g], correct_flags=kw["correct_flags"][:T3g], xy_index_map=kw["xy_index_map"][:T3g])
-    t_g = timed(lambda: ekf_grad_run(plan, x0b, T3g, idx, **kwg), reps=1)
+    t_g = timed(lambda: ekf_grad_run(plan, x0b, T3g, idx, **kwg), reps=2)
     out["c3_hh_loss_and_grad"] = {"param_set_steps_per_s": B3 * T3g / t_g, "sample": f"B={B3} x T={T3g}, p=12 forward-mode",
                                   "alg_tflops": B3 * T3g / t_g * 0.99e6 / 1e12}
     # C4: particle ensemble (reference-parity part: predict only)
     planp = Plan(N.ODE_LORENZ, N.SOLVER_RKF45, 0.01)
     M4, T4 = 1_000_000, 1000
-    t_pf = timed(lambda: pf_run(planp, M4, T4, x0_shared=[1.0, 1.0, 1.0], seed=7, device=dev), reps=1)
+    t_pf = timed(lambda: pf_run(planp, M4, T4, x0_shared=[1.0, 1.0, 1.0], seed=7, device=dev), reps=2)
     out["c4_particle_ensemble"] = {"particle_steps_per_s": M4 * T4 / t_pf, "sample": f"M={M4} x T={T4} (config: T=5000) on 1 GPU"}
     # C5: large-state oscillator chain, n = 256, dense J P J^T on FP64 tensor-core MMAs (DMMA)
     from ode_uncertainty_b200 import ekf_dense_run

@@ -55,16 +55,25 @@ ODEU_HD void save_slot(long long slot, long long B, long long b, int L,
                                           double* out_eps, double* out_P, double* out_yhat,
                                           double* out_S) {
   constexpr int U = (n <= 4) ? n : 1;
+  // one 64-bit multiply per array, then the pointer walks with stride B: the indexed form
+  // (slot * n + i) * B + b cost ~9 instructions per store (ncu: +138 instructions per saved step for
+  // 15 stores, and the streaming variant's time follows its instruction count)
+  if (out_x) {
+    double* p = out_x + slot * n * B + b;
 #pragma unroll U
-  for (int i = 0; i < n; ++i) {
-    if (out_x) out_x[(slot * n + i) * B + b] = x[i];
-    if (out_eps) out_eps[(slot * n + i) * B + b] = eps[i];
+    for (int i = 0; i < n; ++i) { *p = x[i]; p += B; }
+  }
+  if (out_eps) {
+    double* p = out_eps + slot * n * B + b;
+#pragma unroll U
+    for (int i = 0; i < n; ++i) { *p = eps[i]; p += B; }
   }
   if (out_P) {
+    double* p = out_P + slot * (n * n) * B + b;
 #pragma unroll U
     for (int i = 0; i < n; ++i)
 #pragma unroll U
-      for (int j = 0; j < n; ++j) out_P[(slot * n * n + i * n + j) * B + b] = P[i][j];
+      for (int j = 0; j < n; ++j) { *p = P[i][j]; p += B; }
   }
   // y_hat / S of the most recent measurement update were already written into this slot by
   // ObsSink; when no update happened since the previous slot the reference state still holds

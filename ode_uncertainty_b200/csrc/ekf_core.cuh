@@ -45,6 +45,10 @@ enum CovFn { COV_DIAGONAL = 0, COV_OUTER = 1, COV_STATIC_DIAGONAL = 2 };
 struct ScaledTableau {
   double ha[8][8];
   double hb1[8];
+  // unscaled coefficients of the primal sums: as kernel arguments they are constant-bank operands
+  // of the DFMAs; as compile-time immediates each cost two UMOVs per use (50 per Lorenz step)
+  double a[8][8];
+  double b0[8], b1[8];
 };
 
 template <class Ode, class Tab, int KC, class PT>
@@ -77,7 +81,7 @@ ODEU_HD void rk_step_tangent(double t, double h, const ScaledTableau& st, const 
 #pragma unroll
         for (int j = 0; j < i; ++j) {
           if (Tab::a(i, j) != 0.0) {
-            sv = first ? Ks[j][m].v * Tab::a(i, j) : fma(Tab::a(i, j), Ks[j][m].v, sv);
+            sv = first ? Ks[j][m].v * st.a[i][j] : fma(st.a[i][j], Ks[j][m].v, sv);
             first = false;
 #pragma unroll
             for (int k = 0; k < KC; ++k) Xi[m].d[k] = fma(st.ha[i][j], Ks[j][m].d[k], Xi[m].d[k]);
@@ -97,14 +101,14 @@ ODEU_HD void rk_step_tangent(double t, double h, const ScaledTableau& st, const 
 #pragma unroll
     for (int j = 0; j < S; ++j) {
       if (Tab::b(1, j) != 0.0) {
-        s1v = f1 ? Ks[j][m].v * Tab::b(1, j) : fma(Tab::b(1, j), Ks[j][m].v, s1v);
+        s1v = f1 ? Ks[j][m].v * st.b1[j] : fma(st.b1[j], Ks[j][m].v, s1v);
         f1 = false;
 #pragma unroll
         for (int k = 0; k < KC; ++k) Jcols[m][k] = fma(st.hb1[j], Ks[j][m].d[k], Jcols[m][k]);
       }
       if (Tab::b(0, j) != 0.0) {
-        if (f0) { s0 = Ks[j][m].v * Tab::b(0, j); f0 = false; }
-        else s0 = fma(Tab::b(0, j), Ks[j][m].v, s0);
+        if (f0) { s0 = Ks[j][m].v * st.b0[j]; f0 = false; }
+        else s0 = fma(st.b0[j], Ks[j][m].v, s0);
       }
     }
     if (want_primal) {

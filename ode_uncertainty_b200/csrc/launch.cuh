@@ -26,7 +26,12 @@ template <class Tab>
 void fill_scaled_tableau(double h, ScaledTableau& st) {
   for (int i = 0; i < 8; ++i) {
     st.hb1[i] = (i < Tab::S) ? h * Tab::b(1, i) : 0.0;
-    for (int j = 0; j < 8; ++j) st.ha[i][j] = (i < Tab::S && j < Tab::S) ? h * Tab::a(i, j) : 0.0;
+    st.b0[i] = (i < Tab::S) ? Tab::b(0, i) : 0.0;
+    st.b1[i] = (i < Tab::S) ? Tab::b(1, i) : 0.0;
+    for (int j = 0; j < 8; ++j) {
+      st.ha[i][j] = (i < Tab::S && j < Tab::S) ? h * Tab::a(i, j) : 0.0;
+      st.a[i][j] = (i < Tab::S && j < Tab::S) ? Tab::a(i, j) : 0.0;
+    }
   }
 }
 

@@ -1,7 +1,8 @@
 # Builds the C-ABI shared library (sm_100a only) and the CPU oracle.
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC --expt-relaxed-constexpr
+# -cudart shared: the library links libcudart.so instead of carrying a private copy of the runtime
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC --expt-relaxed-constexpr -cudart shared
 CSRC      := ode_uncertainty_b200/csrc
 OBJDIR    := build/obj
 LIB       := ode_uncertainty_b200/libodeu.so
@@ -16,7 +17,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) $(EXTRA) -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+	$(NVCC) $(ARCH) -shared -cudart shared -o $@ $(OBJS)
 
 oracle:
 	$(MAKE) -C oracle

@@ -43,6 +43,11 @@ def parse():
     ap.add_argument("--T", type=int, default=10000, help="steps per trajectory (config: 10000)")
     ap.add_argument("--cpu-sample-B", type=int, default=0, help="CPU baseline sample size (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--guard", default="reference", choices=["reference", "intended"],
+                    help="zero-gain guard of the measurement update: 'reference' = the predicate exactly as "
+                         "src/filters/sqrt_ekf.py:351 writes it (factor-form kernels, results identical to the "
+                         "reference's also where its sign quirk drops observations); 'intended' = all(|S_sqrt| < 1e-16) "
+                         "on the full-covariance kernels")
     return ap.parse_args()
 
 
@@ -136,7 +141,7 @@ def cpu_reference_rate(B_s: int, T_s: int, nthreads: int = 0):
         t = time.perf_counter()
         RC.ekf_run(system, "RKF45", 0.01, w["x0"], T_s, t0=w["t0"], P0_sqrt=w["P0_sqrt"], theta=th,
                    H=w["H"], R_sqrt=w["R_sqrt"], ys=ys, correct_flags=flags, xy_index_map=ymap,
-                   nthreads=cores)
+                   nthreads=cores, count_fragile=False)
         secs += time.perf_counter() - t
         units += B_s * T_s
     return units / secs, cores, f"Lorenz+VanDerPol, B={B_s} trajectories x T={T_s} steps each, Oracle-B sqrt-EKF", secs
@@ -284,7 +289,8 @@ def main():
     def one(system, x0_dev, ys_dev):
         w = inp[system]
         return ekf_run(plans[system], x0_dev, T, t0=w["t0"], P0_sqrt=w["P0_sqrt"], H=w["H"],
-                       R_sqrt=w["R_sqrt"], ys=ys_dev, correct_flags=w["flags"], xy_index_map=w["ymap"])
+                       R_sqrt=w["R_sqrt"], ys=ys_dev, correct_flags=w["flags"], xy_index_map=w["ymap"],
+                       guard=args.guard)
 
     def step_resident():
         return [one(s, inp[s]["x0_dev"], inp[s]["ys_dev"]) for s in ("Lorenz", "VanDerPol")]
@@ -364,12 +370,20 @@ def main():
     units_per_step = 2.0 * B * T * world
     value = units_per_step * args.steps / t_max
     finite = bool(torch.isfinite(r_l.nll).all() and torch.isfinite(r_v.nll).all())
+    # what the zero-gain guard did on this rank's batch in the last timed step (reference mode only):
+    # measurement updates dropped by the predicate as the reference writes it, and updates on which that
+    # predicate and its intended meaning differ (all of them the reference's sign quirk)
+    guard_stats = None
+    if args.guard == "reference":
+        guard_stats = {s_: {"guard_fired_steps": int(r_.guard_fired.sum()), "guard_mismatch_steps": int(r_.guard_mismatch.sum())}
+                       for s_, r_ in (("Lorenz", r_l), ("VanDerPol", r_v))}
 
     # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region
     out_host = {s: (torch.empty(B, inp[s]["n"], dtype=torch.float64).pin_memory(),
-                    torch.empty(B, dtype=torch.float64).pin_memory()) for s in inp}
+                    torch.empty(B, dtype=torch.float64).pin_memory(),
+                    torch.empty(B, inp[s]["n"], inp[s]["n"], dtype=torch.float64).pin_memory()) for s in inp}
     h2d = sum(inp[s]["x0_host"].numel() * 8 + inp[s]["ys_host"].numel() * 8 for s in inp)
-    d2h = sum(out_host[s][0].numel() * 8 + out_host[s][1].numel() * 8 for s in inp)
+    d2h = sum(sum(t_.numel() * 8 for t_ in out_host[s]) for s in inp)     # means, NLL and covariances
 
     def step_e2e():
         for s in ("Lorenz", "VanDerPol"):
@@ -378,6 +392,7 @@ def main():
             r = one(s, x0d, ysd)
             out_host[s][0].copy_(r.xT, non_blocking=True)
             out_host[s][1].copy_(r.nll, non_blocking=True)
+            out_host[s][2].copy_(r.PT, non_blocking=True)
         torch.cuda.synchronize()
 
     step_e2e()
@@ -474,9 +489,10 @@ def main():
             "config": {"workload": "C2", "systems": ["Lorenz", "VanDerPol"], "B_per_gpu": B, "T": T,
                        "solver": "RKF45", "h": 0.01,
                        "observations": "every step, H=I, R=1e-3 I, shared sequence",
+                       "guard": args.guard,
                        "units_per_step": units_per_step, "l2": "flushed (256 MB write) between timed steps",
                        "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
-            "roofline": {"bound": "fp64", "kernel": "ekf_thread_sched_kernel<OdeLorenz,TabRKF45,3,3,64,6>",
+            "roofline": {"bound": "fp64", "kernel": "ekf_thread_sched_kernel<OdeLorenz,TabRKF45,3,3,64,6,%d>" % (1 if args.guard == "reference" else 0),
                          "achieved": achieved, "peak": dfma_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / dfma_peak_tflops,
                          "peak_source": "measured in this run: odeu_bench_dfma (8 DFMA chains/thread, 148x8x256 threads)",
@@ -489,6 +505,7 @@ def main():
             "clocks": clocks,
             "wall_s_timed_region": wall,
             "all_finite": finite,
+            "guard": {"mode": args.guard, "last_step": guard_stats},
             "extras": extras,
         }
         sys.stdout.flush()

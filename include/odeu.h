@@ -138,7 +138,25 @@ typedef struct {
    * parameter set, w from odeu_param_sensitivity.  Replaces Q_sqrt; honoured by odeu_ekf_grad_run
    * (and the NLL-only row kernels of the Hodgkin-Huxley family), rejected by the other kernels. */
   const double* Q_sqrt_diag_batch;  /* DEVICE [n][B] or NULL */
+  /* ---- zero-gain guard of the measurement update (src/filters/sqrt_ekf.py:350-353).
+   * ODEU_GUARD_INTENDED: K = 0 iff all(|S_sqrt| < 1e-16), evaluated on chol(S) by the full-covariance
+   *   kernels (every system size).
+   * ODEU_GUARD_REFERENCE: the predicate exactly as the reference writes it, all(S_sqrt < 1e-16), which
+   *   is also true for a healthy factor whose entries are all negative; S_sqrt carries LAPACK's
+   *   Householder signs (dlarfg), so the run is carried in FACTOR form through the same three QRs per
+   *   step as the reference (sqrt_L_sum_qr, src/utils.py:233-274).  Served for n <= 4 by odeu_ekf_run;
+   *   other kernels reject it.  Results are then the reference's also on inputs where the sign quirk
+   *   drops observations. */
+  int32_t guard_mode;        /* odeu_guard_mode */
+  const double* P0_sqrt_batch; /* DEVICE [n*n][B] per-trajectory FACTOR (resume in reference mode; replaces P0) */
+  double* PT_sqrt;           /* DEVICE [n*n][B] final factor with the reference's signs (reference mode), or NULL */
+  int64_t* guard_counts;     /* DEVICE [2][B] (reference mode) or NULL: measurement updates on which the guard
+                                fired (K = 0); updates on which the verbatim and the intended predicate differ */
 } odeu_ekf_io;
+
+typedef enum { ODEU_GUARD_INTENDED = 0, ODEU_GUARD_REFERENCE = 1,
+               ODEU_GUARD_INTENDED_FACTOR = 2 /* factor-form arithmetic, intended predicate (diagnostics) */
+} odeu_guard_mode;
 
 /* Scratch size for the dynamically scheduled variant of odeu_ekf_run (0 if it does not apply). */
 int64_t odeu_ekf_workspace_bytes(const odeu_plan* plan, int64_t B, int64_t T);

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("ODEU_LIB", os.path.join(_HERE, "libodeu.so"))   # ODE
 ODE_LORENZ, ODE_VAN_DER_POL, ODE_LOTKA_VOLTERRA, ODE_PENDULUM, ODE_LCAO, ODE_HODGKIN_HUXLEY, ODE_MULTI_HH = range(7)
 SOLVER_RKF45, SOLVER_DOPRI65, SOLVER_BS32, SOLVER_HEUN_EULER = range(4)
 COV_DIAGONAL, COV_OUTER, COV_STATIC_DIAGONAL = range(3)
+GUARD_INTENDED, GUARD_REFERENCE, GUARD_INTENDED_FACTOR = range(3)
 
 # every symbol include/odeu.h declares (tests assert the library exports all of them)
 SYMBOLS = (
@@ -49,6 +50,7 @@ class EkfIO(C.Structure):
         ("tT", _dp), ("out_t", _dp), ("out_x", _dp), ("out_eps", _dp), ("out_P", _dp),
         ("out_yhat", _dp), ("out_S", _dp), ("cov_scale_batch", _dp), ("nll_nan_to_num", C.c_int32),
         ("Q_sqrt_diag_batch", _dp),
+        ("guard_mode", C.c_int32), ("P0_sqrt_batch", _dp), ("PT_sqrt", _dp), ("guard_counts", _dp),
     ]
 
 

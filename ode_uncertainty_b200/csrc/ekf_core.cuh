@@ -42,6 +42,8 @@ enum CovFn { COV_DIAGONAL = 0, COV_OUTER = 1, COV_STATIC_DIAGONAL = 2 };
 // Tangent lanes carry no cancellation, so they accumulate straight into the identity seed with
 // the pre-scaled coefficients ha[i][j] = h a_ij, hb1[j] = h b_1j (kernel arguments, i.e.
 // constant-bank operands of the DFMAs): one DFMA per non-zero coefficient, no separate h-scale.
+// `seed` (optional, [n][KC]): tangent seeds instead of identity columns - the factor form seeds
+// with the columns of P_sqrt like jmp_aux (src/utils.py:72-79), so Jcols returns T = J P_sqrt.
 struct ScaledTableau {
   double ha[8][8];
   double hb1[8];
@@ -54,7 +56,7 @@ struct ScaledTableau {
 template <class Ode, class Tab, int KC, class PT>
 ODEU_HD void rk_step_tangent(double t, double h, const ScaledTableau& st, const double* x,
                              const PT* th, int c0, bool want_primal, double* xn, double* eps,
-                             double (*Jcols)[KC]) {
+                             double (*Jcols)[KC], const double (*seed)[KC] = nullptr) {
   constexpr int n = Ode::NX;
   constexpr int S = Tab::S;
   using D = Dual<KC>;
@@ -63,7 +65,7 @@ ODEU_HD void rk_step_tangent(double t, double h, const ScaledTableau& st, const 
   for (int m = 0; m < n; ++m) {
     X[m].v = x[m];
 #pragma unroll
-    for (int k = 0; k < KC; ++k) X[m].d[k] = (m == c0 + k) ? 1.0 : 0.0;
+    for (int k = 0; k < KC; ++k) X[m].d[k] = seed ? seed[m][k] : ((m == c0 + k) ? 1.0 : 0.0);
   }
   D Ks[S][n];
 #pragma unroll
@@ -322,7 +324,7 @@ ODEU_HD double correct_step(int L, const double* H, const double* R,
           double v = Smat[i][j];
 #pragma unroll U
           for (int k = 0; k < j; ++k) v = fma(-Ls[i][k], Ls[j][k], v);
-          v *= inv[j];
+          v = (dj == 0.0) ? 0.0 : v * inv[j];    // exactly singular S: a zero column, not 0 * inf
           Ls[i][j] = v;
           all_tiny = all_tiny && (fabs(v) < 1e-16);
         }
@@ -501,7 +503,8 @@ ODEU_HD double correct_step_lead(const double* R, const double* y, double* x, do
     for (int k = 0; k < j; ++k) s = fma(-Ls[j][k], Ls[j][k], s);
     piv *= s;
     const double r = rsqrt(s);
-    const double dj = s * r;             // sqrt(s) up to an ulp; NaN for s < 0 like sqrt
+    const double dj = (s == 0.0) ? 0.0 : s * r;   // sqrt(s) up to an ulp; NaN for s < 0 like sqrt; an exactly
+                                         // singular S (P = 0, R = 0) must trip the guard, not poison it (0 * inf)
     inv[j] = r;
     Ls[j][j] = dj;
     all_tiny = all_tiny && (fabs(dj) < 1e-16);
@@ -510,7 +513,7 @@ ODEU_HD double correct_step_lead(const double* R, const double* y, double* x, do
       double v = Smat[i][j];
 #pragma unroll
       for (int k = 0; k < j; ++k) v = fma(-Ls[i][k], Ls[j][k], v);
-      v *= r;
+      v = (s == 0.0) ? 0.0 : v * r;        // exactly singular S: a zero column, not 0 * inf
       Ls[i][j] = v;
       all_tiny = all_tiny && (fabs(v) < 1e-16);
     }

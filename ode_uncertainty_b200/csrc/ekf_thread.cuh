@@ -13,6 +13,7 @@
 //   xT [n][B]  epsT [n][B]  PT [n*n][B]  yhatT [L][B]  ST [L*L][B]  nll [B]  tT [1]
 #pragma once
 #include "ekf_core.cuh"
+#include "ekf_sqrt.cuh"
 
 namespace odeu {
 
@@ -46,6 +47,15 @@ struct EkfArgs {
   double R[NX * NX];      // [L][L] = R_sqrt R_sqrt^T
   double theta_shared[NP];
   ScaledTableau st;       // h * a_ij, h * b_1j
+  // ---- guard mode "reference" (factor form, ekf_sqrt.cuh; small systems only)
+  static constexpr int NF = (NX <= 4) ? NX * NX : 1;
+  int guard_verbatim;     // 1: `all(S_sqrt < 1e-16)` as written (sqrt_ekf.py:351); 0: intended |.|
+  const double* P0f_b;    // nullable: per-trajectory factor [n*n][B] (resume)
+  double* PsT;            // nullable: final factor [n*n][B]
+  long long* guard_counts;  // nullable: [2][B] steps the guard fired / steps the two predicates differ
+  double P0f[NF];         // shared P0_sqrt
+  double GQs[NF];         // gamma_sqrt * Q_sqrt
+  double Rs[NF];          // R_sqrt [L][L]
 };
 
 template <int n>
@@ -107,7 +117,10 @@ ODEU_HD double ws_load(const double* p) {
 struct Segment {
   long long step0, step1;   // steps of this segment
   bool first, last;         // first: state comes from x0/P0/t0; last: final outputs are written
-  double* ws;               // [n + n*n + 1][B] state, then t per block of 32 trajectories
+  double* ws;               // [n + n*n + 2][B] state (x, P or factor, nll, guard counters), then t per
+                            // block of 32 trajectories
+  const long long* last_obs;  // nullable: last step with an observation, found once per launch
+                            // (find_last_obs_kernel); null = this trajectory scans the flags itself
 };
 
 // jnp.nan_to_num of one log-likelihood term (calibration sweep, :218 of the calibration script)
@@ -119,7 +132,10 @@ ODEU_HD double nll_term(double v, int nan_to_num) {
   return v;
 }
 
-template <class Ode, class Tab, int KC, int LK>
+// SQ selects the covariance representation: 0 = full P (intended guard), 1 = factor form with the
+// structured QRs (H = [I_LK 0], lower-triangular R_sqrt, diagonal process-noise block), 2 = factor
+// form, generic.  In the factor forms `P` below holds P_sqrt.
+template <class Ode, class Tab, int KC, int LK, int SQ = 0>
 ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long b, const Segment& sg) {
   constexpr int n = Ode::NX;
   const double cov_scale = a.scale_b ? a.scale_b[b] : a.cov_scale;
@@ -132,13 +148,21 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   double t, nll;
   LogProd lp;              // deferred log-determinant terms of this segment
   lp.reset();
+  GuardCount gc = {0, 0};
   if (sg.first) {
 #pragma unroll U
     for (int i = 0; i < n; ++i) x[i] = a.x0[i * B + b];
+    if constexpr (SQ != 0) {
+#pragma unroll U
+      for (int i = 0; i < n; ++i)
+#pragma unroll U
+        for (int j = 0; j < n; ++j) P[i][j] = a.P0f_b ? a.P0f_b[(i * n + j) * B + b] : a.P0f[i * n + j];
+    } else {
 #pragma unroll U
     for (int i = 0; i < n; ++i)
 #pragma unroll U
       for (int j = 0; j < n; ++j) P[i][j] = a.P0 ? a.P0[(i * n + j) * B + b] : a.P0s[i * n + j];
+    }
     // final-state y_hat / S start at zero like SQRT_EKF.init_state (sqrt_ekf.py:80-82)
     for (int l = 0; l < L; ++l)
       if (a.yhatT) a.yhatT[l * B + b] = 0.0;
@@ -149,6 +173,15 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   } else {
 #pragma unroll U
     for (int i = 0; i < n; ++i) x[i] = ws_load(sg.ws + i * B + b);
+    if constexpr (SQ != 0) {
+#pragma unroll U
+      for (int i = 0; i < n; ++i)
+#pragma unroll U
+        for (int j = 0; j < n; ++j) P[i][j] = ws_load(sg.ws + (n + i * n + j) * B + b);
+      const long long packed = LogProd::to_bits(ws_load(sg.ws + (n + n * n + 1) * B + b));
+      gc.fired = (int)(packed & 0xffffffffLL);
+      gc.mismatch = (int)(packed >> 32);
+    } else {
 #pragma unroll U
     for (int i = 0; i < n; ++i)
 #pragma unroll U
@@ -157,8 +190,9 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
         P[i][j] = v;
         P[j][i] = v;
       }
+    }
     nll = ws_load(sg.ws + (n + n * n) * B + b);
-    t = ws_load(sg.ws + (n + n * n + 1) * B + (b >> 5));
+    t = ws_load(sg.ws + (n + n * n + 2) * B + (b >> 5));
   }
 #pragma unroll U
   for (int i = 0; i < n; ++i) eps[i] = 0.0;
@@ -169,6 +203,11 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   const double h = a.h;
   const long long si = a.save_interval;
   if (si > 0 && sg.first) {
+    if constexpr (SQ != 0) {
+      double Pc[n][n];
+      factor_to_cov<n>(P, Pc);
+      save_slot<n>(0, B, b, L, x, eps, Pc, false, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+    } else
     save_slot<n>(0, B, b, L, x, eps, P, false, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
     if (b == 0 && a.out_t) a.out_t[0] = t;
   }
@@ -177,12 +216,21 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   // The final-state y_hat / S are those of the LAST measurement update of the run (the reference
   // state dict simply keeps them, sqrt_ekf.py:370-372).  Publishing them at every observation step
   // cost L + L^2 global stores per step (12 of the 12.1 stores per step at C2, +2.5 % run time), so
-  // only the step that is the last observation writes them: scan the flags backwards once (one
-  // load when every step is observed; a segment stops at its own first step).
+  // only the step that is the last observation writes them.  The dynamic scheduler finds that step
+  // once per launch (find_last_obs_kernel); a static launch scans the flags backwards once per
+  // trajectory (one load when every step is observed).
   long long last_obs = -1;
   if (LK != 0 && a.has_obs && (a.yhatT || a.ST)) {
-    for (long long s = a.T - 1; s >= sg.step0; --s)
-      if (a.flags[s]) { last_obs = s; break; }
+    if (sg.last_obs) {
+#ifdef __CUDA_ARCH__
+      last_obs = __ldg(sg.last_obs);
+#else
+      last_obs = *sg.last_obs;
+#endif
+    } else {
+      for (long long s = a.T - 1; s >= sg.step0; --s)
+        if (a.flags[s]) { last_obs = s; break; }
+    }
   }
 
   for (long long step = sg.step0; step < sg.step1; ++step) {
@@ -191,7 +239,11 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     if (LK == -1 && a.skip_predict) {
       // single-step FilterCorrect: leave t, x, eps, P untouched
     } else {
-    if constexpr (KC == n) {
+    if constexpr (SQ != 0) {
+      // tangents seeded with the columns of P_sqrt like jmp_aux (src/utils.py:72-79): J holds T = J P_sqrt
+      static_assert(SQ == 0 || KC == n, "factor form carries all tangent columns in one pass");
+      rk_step_tangent<Ode, Tab, KC>(t, h, a.st, x, th, 0, true, xn, eps, J, P);
+    } else if constexpr (KC == n) {
       rk_step_tangent<Ode, Tab, KC>(t, h, a.st, x, th, 0, true, xn, eps, J);
     } else {
 #pragma unroll 1
@@ -205,8 +257,17 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
             if (c0 + k < n) J[i][c0 + k] = Jc[i][k];
       }
     }
+    if constexpr (SQ == 1) {
+      double e[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) e[i] = (a.cov_fn == COV_STATIC_DIAGONAL) ? cov_scale : cov_scale * eps[i];
+      predict_factor_diag<n>(J, e, P);
+    } else if constexpr (SQ == 2) {
+      predict_factor_generic<n>(a.noise_mode, a.cov_fn, cov_scale, eps, a.GQs, J, P);
+    } else {
     propagate_cov<n>(J, P);
     add_process_noise<n>(a.noise_mode, a.cov_fn, cov_scale, eps, a.GQ, P);
+    }
 #pragma unroll U
     for (int i = 0; i < n; ++i) x[i] = xn[i];
     t = t + h;  // accumulated like rksolver.py:145 (stage times depend on it)
@@ -232,6 +293,9 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 #pragma unroll U
         for (int l = 0; l < n; ++l)
           if (l < L) y[l] = a.ys_per_traj ? a.ys[(oi * L + l) * B + b] : a.ys[oi * L + l];
+        if constexpr (SQ != 0)
+          nll += nll_term(correct_factor_generic<n>(L, a.H, a.Rs, y, x, P, sink, a.guard_verbatim != 0, gc), a.nan_to_num);
+        else
         nll += nll_term(correct_step<n>(L, a.H, a.R, y, x, P, sink), a.nan_to_num);
         obs_fresh = true;
       }
@@ -243,6 +307,10 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
         double y[LK];
 #pragma unroll
         for (int l = 0; l < LK; ++l) y[l] = yp[l * ystr];
+        if constexpr (SQ == 1)
+          nll += nll_term(correct_factor_lead<n, LK>(a.R, a.Rs, y, x, P, sink, a.nan_to_num ? nullptr : &lp,
+                                                     a.guard_verbatim != 0, gc), a.nan_to_num);
+        else
         nll += nll_term(correct_step_lead<n, LK>(a.R, y, x, P, sink, a.nan_to_num ? nullptr : &lp), a.nan_to_num);
         obs_fresh = true;
       }
@@ -250,6 +318,11 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
 
     // ---- strided save (scripts/run_filter.py:219-222)
     if (si > 0 && step + 1 == next_save) {
+      if constexpr (SQ != 0) {
+        double Pc[n][n];
+        factor_to_cov<n>(P, Pc);
+        save_slot<n>(slot, B, b, L, x, eps, Pc, obs_fresh, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+      } else
       save_slot<n>(slot, B, b, L, x, eps, P, obs_fresh, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
       obs_fresh = false;
       if (b == 0 && a.out_t) a.out_t[slot] = t;
@@ -261,12 +334,21 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   if (!sg.last) {   // hand the state to whoever runs the next segment
 #pragma unroll U
     for (int i = 0; i < n; ++i) sg.ws[i * B + b] = x[i];
+    if constexpr (SQ != 0) {
+#pragma unroll U
+      for (int i = 0; i < n; ++i)
+#pragma unroll U
+        for (int j = 0; j < n; ++j) sg.ws[(n + i * n + j) * B + b] = P[i][j];
+      sg.ws[(n + n * n + 1) * B + b] =
+          LogProd::from_bits(((long long)gc.mismatch << 32) | (long long)(unsigned)gc.fired);
+    } else {
 #pragma unroll U
     for (int i = 0; i < n; ++i)
 #pragma unroll U
       for (int j = 0; j <= i; ++j) sg.ws[(n + i * n + j) * B + b] = P[i][j];
+    }
     sg.ws[(n + n * n) * B + b] = nll + lp.flush();
-    if ((b & 31) == 0) sg.ws[(n + n * n + 1) * B + (b >> 5)] = t;
+    if ((b & 31) == 0) sg.ws[(n + n * n + 2) * B + (b >> 5)] = t;
     return;
   }
   // ---- final state
@@ -275,6 +357,26 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     if (a.xT) a.xT[i * B + b] = x[i];
     if (a.epsT) a.epsT[i * B + b] = eps[i];
   }
+  if constexpr (SQ != 0) {
+    if (a.PsT) {
+#pragma unroll U
+      for (int i = 0; i < n; ++i)
+#pragma unroll U
+        for (int j = 0; j < n; ++j) a.PsT[(i * n + j) * B + b] = P[i][j];
+    }
+    if (a.PT) {
+      double Pc[n][n];
+      factor_to_cov<n>(P, Pc);
+#pragma unroll U
+      for (int i = 0; i < n; ++i)
+#pragma unroll U
+        for (int j = 0; j < n; ++j) a.PT[(i * n + j) * B + b] = Pc[i][j];
+    }
+    if (a.guard_counts) {
+      a.guard_counts[b] = gc.fired;
+      a.guard_counts[B + b] = gc.mismatch;
+    }
+  } else
   if (a.PT) {
 #pragma unroll U
     for (int i = 0; i < n; ++i)
@@ -285,13 +387,22 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   if (b == 0 && a.tT) a.tT[0] = t;
 }
 
-template <class Ode, class Tab, int KC, int LK, int BLOCK, int MINB>
+template <class Ode, class Tab, int KC, int LK, int BLOCK, int MINB, int SQ = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
 ekf_thread_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a) {
   const long long b = (long long)blockIdx.x * BLOCK + threadIdx.x;
   if (b >= a.B) return;
-  const Segment whole = {0, a.T, true, true, nullptr};
-  ekf_trajectory<Ode, Tab, KC, LK>(a, b, whole);
+  const Segment whole = {0, a.T, true, true, nullptr, nullptr};
+  ekf_trajectory<Ode, Tab, KC, LK, SQ>(a, b, whole);
+}
+
+// last step that carries an observation (-1: none): one thread, scanned once per run instead of by
+// every thread of every time segment
+static __global__ void find_last_obs_kernel(const unsigned char* flags, long long T, long long* out) {
+  long long last = -1;
+  for (long long s = T - 1; s >= 0; --s)
+    if (flags[s]) { last = s; break; }
+  *out = last;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -310,9 +421,10 @@ struct SchedArgs {
   double* ws;                // state workspace (see Segment)
   int* counter;              // next work item
   int* done;                 // [nblk] number of published segments per block
+  const long long* last_obs; // nullable (no observations): see Segment
 };
 
-template <class Ode, class Tab, int KC, int LK, int BLOCK, int MINB>
+template <class Ode, class Tab, int KC, int LK, int BLOCK, int MINB, int SQ = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
 ekf_thread_sched_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a,
                         const __grid_constant__ SchedArgs s) {
@@ -341,7 +453,8 @@ ekf_thread_sched_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a,
       sg.first = seg == 0;
       sg.last = seg + 1 == s.nseg;
       sg.ws = s.ws;
-      ekf_trajectory<Ode, Tab, KC, LK>(a, b, sg);
+      sg.last_obs = s.last_obs;
+      ekf_trajectory<Ode, Tab, KC, LK, SQ>(a, b, sg);
     }
     __threadfence();
     __syncwarp();

@@ -42,7 +42,25 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
   if (io.B <= 0 || io.T < 0) { set_error("odeu_ekf_run: B must be > 0 and T >= 0"); return -1; }
   if (io.L < 0 || io.L > n) { set_error("odeu_ekf_run: L=%d outside [0, n=%d]", io.L, n); return -1; }
   if (!io.x0) { set_error("odeu_ekf_run: x0 is required"); return -1; }
-  if (!io.P0 && !io.P0_sqrt) { set_error("odeu_ekf_run: P0 or P0_sqrt is required"); return -1; }
+  if (!io.P0 && !io.P0_sqrt && !io.P0_sqrt_batch) { set_error("odeu_ekf_run: P0, P0_sqrt or P0_sqrt_batch is required"); return -1; }
+  if (io.guard_mode < ODEU_GUARD_INTENDED || io.guard_mode > ODEU_GUARD_INTENDED_FACTOR) {
+    set_error("odeu_ekf_run: unknown guard_mode %d", io.guard_mode);
+    return -1;
+  }
+  const bool factor = io.guard_mode != ODEU_GUARD_INTENDED;
+  if (factor && n > 4) {
+    set_error("odeu_ekf_run: guard_mode reference (factor form) is served for state dimension <= 4, this plan has n = %d", n);
+    return -2;
+  }
+  if (factor && io.P0 && !io.P0_sqrt_batch) {
+    set_error("odeu_ekf_run: guard_mode reference resumes from the FACTOR (P0_sqrt_batch = a previous PT_sqrt), not from P0");
+    return -1;
+  }
+  if (!factor && (io.P0_sqrt_batch || io.PT_sqrt || io.guard_counts)) {
+    set_error("odeu_ekf_run: P0_sqrt_batch / PT_sqrt / guard_counts need guard_mode reference (factor form)");
+    return -1;
+  }
+
   if (io.save_interval < 0) { set_error("odeu_ekf_run: save_interval < 0"); return -1; }
   if (io.Q_sqrt_diag_batch) {
     set_error("odeu_ekf_run: the per-trajectory diagonal Q_sqrt (parameter_sensitivity) is served by odeu_ekf_grad_run");
@@ -63,6 +81,8 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
   a.xT = io.xT; a.epsT = io.epsT; a.PT = io.PT; a.yhatT = io.yhatT; a.ST = io.ST; a.nll = io.nll;
   a.scale_b = io.cov_scale_batch; a.nan_to_num = io.nll_nan_to_num;
   a.tT = io.tT;
+  a.guard_verbatim = io.guard_mode == ODEU_GUARD_REFERENCE ? 1 : 0;
+  a.P0f_b = io.P0_sqrt_batch; a.PsT = io.PT_sqrt; a.guard_counts = (long long*)io.guard_counts;
   a.out_t = io.out_t; a.out_x = io.out_x; a.out_eps = io.out_eps; a.out_P = io.out_P;
   a.out_yhat = io.out_yhat; a.out_S = io.out_S;
 
@@ -100,6 +120,14 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
   }
   for (int k = 0; k < NP; ++k)
     a.theta_shared[k] = io.theta_shared ? io.theta_shared[k] : plan.theta_default[k];
+  if constexpr (n <= 4) {    // factor form: the factors themselves
+    for (int i = 0; i < n * n; ++i) {
+      a.P0f[i] = io.P0_sqrt ? io.P0_sqrt[i] : 0.0;
+      a.GQs[i] = io.Q_sqrt ? io.gamma_sqrt * io.Q_sqrt[i] : 0.0;
+      a.Rs[i] = 0.0;
+    }
+    for (int i = 0; i < L * L; ++i) a.Rs[i] = io.R_sqrt[i];
+  }
   return 0;
 }
 
@@ -139,20 +167,21 @@ inline bool sched_geometry(int n, long long B, long long T, SchedGeom& g) {
   g.seg_len = (T + nseg_target - 1) / nseg_target;
   if (g.seg_len < 64) g.seg_len = 64;
   g.nseg = (T + g.seg_len - 1) / g.seg_len;
-  g.state_doubles = (long long)(n + n * n + 1) * B + g.nblk;
+  g.state_doubles = (long long)(n + n * n + 2) * B + g.nblk + 1;   // + 1: last observation step
   g.bytes = g.state_doubles * 8 + (1 + g.nblk) * 4 + 64;
   // worth it only when every SM sub-partition holds several warps and there are several segments
   return n <= 4 && g.nseg >= 4 && g.nblk >= 4LL * sm_count();
 }
 
-template <class Ode, class Tab, int LK>
+template <class Ode, class Tab, int LK, int SQ = 0>
 int launch_ekf_variant(const EkfArgs<Ode::NX, Ode::NP>& a, const odeu_ekf_io& io, cudaStream_t stream) {
   using Cfg = LaunchCfg<Ode>;
   SchedGeom g;
   // measured on B200 (tools/sched_sweep.py): +7..12 % with the measurement update (Lorenz 16.1 ->
   // 17.6, Van der Pol 32.4 -> 36.3 G trajectory-steps/s); prediction-only runs are faster with the
   // static launch (32.1 vs 27.3), so LK == 0 keeps it
-  if (LK != 0 && io.workspace && io.save_interval == 0 && !io.skip_predict &&
+  if constexpr (LK != 0 && SQ != 2)     // (the generic factor form keeps the static launch)
+  if (io.workspace && io.save_interval == 0 && !io.skip_predict &&
       sched_geometry(Ode::NX, a.B, a.T, g) && io.workspace_bytes >= g.bytes) {
     SchedArgs s;
     s.seg_len = g.seg_len; s.nseg = g.nseg; s.nblk = g.nblk;
@@ -161,18 +190,37 @@ int launch_ekf_variant(const EkfArgs<Ode::NX, Ode::NP>& a, const odeu_ekf_io& io
     s.done = s.counter + 1;
     cudaError_t e = cudaMemsetAsync(s.counter, 0, (1 + g.nblk) * 4, stream);
     if (e != cudaSuccess) { set_error("odeu_ekf_run: workspace memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    long long* last_obs = (long long*)io.workspace + (g.state_doubles - 1);
+    s.last_obs = nullptr;
+    if (a.has_obs && (a.yhatT || a.ST)) {
+      find_last_obs_kernel<<<1, 1, 0, stream>>>(a.flags, a.T, last_obs);
+      s.last_obs = last_obs;
+    }
     long long resident = (long long)sm_count() * Cfg::MINB;     // one CTA per register slot
     static const int cap = getenv("ODEU_SCHED_CAP") ? atoi(getenv("ODEU_SCHED_CAP")) : 1;       // tuning knob
     const long long useful = (g.nblk * 32 + Cfg::BLOCK - 1) / Cfg::BLOCK;  // more warps than blocks only spin
     if (cap && resident > useful) resident = useful;
-    ekf_thread_sched_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB>
+    ekf_thread_sched_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB, SQ>
         <<<(unsigned)resident, Cfg::BLOCK, 0, stream>>>(a, s);
     return 0;
   }
   const long long grid = (a.B + Cfg::BLOCK - 1) / Cfg::BLOCK;
-  ekf_thread_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB>
+  ekf_thread_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB, SQ>
       <<<(unsigned)grid, Cfg::BLOCK, 0, stream>>>(a);
   return 0;
+}
+
+// Factor form (guard_mode reference): the structured variant needs H = [I_L 0] (LK > 0), the
+// NOISE_COVFN branch with a diagonal process-noise block and a lower-triangular R_sqrt; everything
+// else takes the generic factor code.
+template <class Ode>
+bool factor_fast_ok(const EkfArgs<Ode::NX, Ode::NP>& a, const odeu_ekf_io& io, int lk) {
+  if (lk <= 0) return false;
+  if (a.noise_mode != NOISE_COVFN || a.cov_fn == COV_OUTER) return false;
+  for (int l = 0; l < io.L; ++l)
+    for (int m = l + 1; m < io.L; ++m)
+      if (io.R_sqrt[l * io.L + m] != 0.0) return false;
+  return true;
 }
 
 template <class Ode, class Tab>
@@ -184,6 +232,14 @@ int launch_ekf(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream
   const int lk = select_lk<Ode>(io);
   int rc = 0;
   if constexpr (n <= 4) {
+    if (io.guard_mode != ODEU_GUARD_INTENDED) {
+      if (factor_fast_ok<Ode>(a, io, lk)) {
+        if (lk == 1) rc = launch_ekf_variant<Ode, Tab, 1, 1>(a, io, stream);
+        else rc = launch_ekf_variant<Ode, Tab, n, 1>(a, io, stream);
+      } else {
+        rc = launch_ekf_variant<Ode, Tab, -1, 2>(a, io, stream);
+      }
+    } else
     if (lk == 0) rc = launch_ekf_variant<Ode, Tab, 0>(a, io, stream);
     else if (lk == 1) rc = launch_ekf_variant<Ode, Tab, 1>(a, io, stream);
     else if (lk == n) rc = launch_ekf_variant<Ode, Tab, n>(a, io, stream);

@@ -78,6 +78,16 @@ class EkfResult:
     yhatT: Optional[torch.Tensor] = None   # [B, L]
     ST: Optional[torch.Tensor] = None      # [B, L, L]
     traj: Optional[Dict[str, torch.Tensor]] = None  # t [Ts], x/eps [Ts,B,n], P [Ts,B,n,n], y_hat [Ts,B,L], S [Ts,B,L,L]
+    # guard="reference" only (factor form): the final factor with the reference's Householder signs, the
+    # number of measurement updates on which the zero-gain guard fired, and on which the verbatim and the
+    # intended predicate differ
+    PT_sqrt: Optional[torch.Tensor] = None        # [B, n, n]
+    guard_fired: Optional[torch.Tensor] = None    # [B] int64
+    guard_mismatch: Optional[torch.Tensor] = None  # [B] int64
+
+
+GUARD_MODES = {"intended": N.GUARD_INTENDED, "reference": N.GUARD_REFERENCE,
+               "intended_factor": N.GUARD_INTENDED_FACTOR}
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -94,12 +104,18 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             save_keys=("t", "x", "eps", "P", "y_hat", "S"), want_final: bool = True,
             skip_predict: bool = False, dynamic: bool = True, minimal: bool = False,
             cov_scale_batch: Optional[torch.Tensor] = None, nll_nan_to_num: bool = False,
-            stream: Optional[torch.cuda.Stream] = None) -> EkfResult:
+            stream: Optional[torch.cuda.Stream] = None, guard: str = "intended",
+            P0_sqrt_batch: Optional[torch.Tensor] = None) -> EkfResult:
     """Run T EKF steps for a batch of trajectories.
 
     x0 [B, n] (CUDA, float64); P0 [B, n, n] per-trajectory covariance or P0_sqrt [n, n] shared
     factor (host); theta [B, p] per-trajectory parameters; ys [T_obs, L] shared or
     [T_obs, B, L] per trajectory; correct_flags [T] bool/uint8; xy_index_map [T] int64.
+
+    guard: "intended" (zero gain iff all(|S_sqrt| < 1e-16); full-covariance kernels) or "reference"
+    (the predicate exactly as src/filters/sqrt_ekf.py:351 writes it, all(S_sqrt < 1e-16), on a factor
+    with LAPACK's Householder signs; factor-form kernel, n <= 4; resume with P0_sqrt_batch = a previous
+    result's PT_sqrt).
     """
     _require_cuda(x0, "x0")
     dev = x0.device
@@ -112,8 +128,15 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
     if P0 is not None:
         _require_cuda(P0, "P0")
         P0_k = P0.to(torch.float64).reshape(B, n * n).t().contiguous()  # [n*n][B]
+    if guard not in GUARD_MODES:
+        raise ValueError(f"guard must be one of {sorted(GUARD_MODES)}, got {guard!r}")
+    factor = guard != "intended"
+    P0f_k = None
+    if P0_sqrt_batch is not None:
+        _require_cuda(P0_sqrt_batch, "P0_sqrt_batch")
+        P0f_k = P0_sqrt_batch.to(torch.float64).reshape(B, n * n).t().contiguous()  # [n*n][B]
     P0s_h = _host(P0_sqrt, (n, n)) if P0_sqrt is not None else None
-    if P0_k is None and P0s_h is None:
+    if P0_k is None and P0s_h is None and P0f_k is None:
         P0s_h = np.eye(n) * 1e-12   # default of scripts/run_filter.py:74-78
     th_k = None
     if theta is not None:
@@ -158,8 +181,9 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
         _require_cuda(cov_scale_batch, "cov_scale_batch")
         scale_k = cov_scale_batch.to(torch.float64).reshape(B).contiguous()
     io.cov_scale_batch, io.nll_nan_to_num = _dev(scale_k), int(bool(nll_nan_to_num))
+    io.guard_mode, io.P0_sqrt_batch = GUARD_MODES[guard], _dev(P0f_k)
     ws = None
-    if dynamic and save_interval == 0 and not skip_predict and P0_k is None:
+    if dynamic and save_interval == 0 and not skip_predict and P0_k is None and P0f_k is None:
         wsb = int(N.lib().odeu_ekf_workspace_bytes(plan.handle, B, int(T)))
         if wsb > 0:   # large throughput runs: dynamic (block, time-segment) scheduling
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -179,6 +203,12 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             ST = torch.zeros(L * L, B, **f64)
     io.xT, io.epsT, io.PT, io.yhatT, io.ST = _dev(xT), _dev(epsT), _dev(PT), _dev(yT), _dev(ST)
     io.nll, io.tT = _dev(nll), _dev(tT)
+    PsT = gcount = None
+    if factor:
+        if want_final:
+            PsT = torch.empty(n * n, B, **f64)
+        gcount = torch.zeros(2, B, dtype=torch.int64, device=dev)
+        io.PT_sqrt, io.guard_counts = _dev(PsT), _dev(gcount)
 
     tr = {}
     if save_interval > 0:
@@ -220,7 +250,10 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
         PT=None if PT is None else PT.t().reshape(B, n, n), nll=nll,
         tT=None if tT is None else tT[0],
         yhatT=None if yT is None else yT.t(),
-        ST=None if ST is None else ST.t().reshape(B, L, L), traj=traj)
+        ST=None if ST is None else ST.t().reshape(B, L, L), traj=traj,
+        PT_sqrt=None if PsT is None else PsT.t().reshape(B, n, n),
+        guard_fired=None if gcount is None else gcount[0],
+        guard_mismatch=None if gcount is None else gcount[1])
 
 
 def ekf_grad_run(plan: Plan, x0: torch.Tensor, T: int, grad_idx, *, t0: float = 0.0, P0_sqrt=None,

@@ -226,32 +226,74 @@ void rk_step(const OdeSpec& o, const Tableau& tb, double h, double t, const T* x
 
 // ---------------------------------------------------------------- Householder QR, R only
 // A is m x n row-major (m >= n).  On return the upper triangle of the first n rows holds R with
-// LAPACK dgeqr2/dlarfg signs: beta = -sign(alpha) * norm (alpha == 0 counts as positive).
-void householder_R(double* A, int m, int n) {
+// LAPACK dgeqr2/dlarfg signs: beta = -sign(alpha) * norm (Fortran SIGN: the sign BIT of alpha);
+// a sub-column that is STRUCTURALLY zero gives H = I, beta = alpha (dlarfg, xnorm == 0).
+//
+// Fragile columns.  The sign of R_jj is -sign(alpha_j) when the sub-column is non-zero and
+// +sign(alpha_j) when it is exactly zero.  When the columns of the stacked matrix are (nearly)
+// collinear - a covariance that has collapsed onto fewer directions than n, e.g. Van der Pol with
+// observation noise >> process noise - the sub-column after the earlier reflectors is pure
+// cancellation noise, and whether that noise is exactly 0.0 or 1e-22 depends on the BLAS build
+// (FMA or not, accumulation order): the reference's OWN sign, and with it the guard
+// `all(S_sqrt < 1e-16)`, is then decided by rounding.  Measured against LAPACK (torch.linalg.qr,
+// tests/test_guard_reference.py): the generic outcome is "noise != 0".  This routine therefore
+//   (a) treats a sub-column that CANCELLED to exactly zero (entries that received non-zero update
+//       terms) like noise: beta = -sign(alpha) |alpha|, i.e. the reflector flips row j, and
+//   (b) counts every column whose sub-column norm is at the rounding level of the terms that
+//       produced it (<= 1e3 ulp) in *fragile, so a parity run can tell "sign decided by
+//       arithmetic" from "sign decided by rounding".
+void householder_R(double* A, int m, int n, long long* fragile = nullptr) {
+  // touched[i][k]: entry received a non-zero update term (tells "cancelled to zero" from "never set");
+  // Mg (only when counting fragile columns): magnitude of the terms each entry was built from
+  std::vector<unsigned char> touched((size_t)m * n, 0);
+  std::vector<double> Mg;
+  if (fragile) { Mg.resize((size_t)m * n); for (int i = 0; i < m * n; ++i) Mg[i] = std::fabs(A[i]); }
   for (int j = 0; j < n; ++j) {
-    double xnorm2 = 0.0;
-    for (int i = j + 1; i < m; ++i) xnorm2 += A[i * n + j] * A[i * n + j];
+    double xnorm2 = 0.0, mg2 = 0.0;
+    bool any_touched = false;
+    for (int i = j + 1; i < m; ++i) {
+      xnorm2 += A[i * n + j] * A[i * n + j];
+      any_touched = any_touched || touched[i * n + j];
+      if (fragile) mg2 += Mg[i * n + j] * Mg[i * n + j];
+    }
     const double alpha = A[j * n + j];
-    if (xnorm2 == 0.0) continue;  // dlarfg: H = I, beta = alpha
+    if (fragile && mg2 > 0.0 && xnorm2 <= (1e3 * 1.1e-16) * (1e3 * 1.1e-16) * mg2) ++*fragile;
+    if (xnorm2 == 0.0) {
+      if (!any_touched) continue;              // structurally zero: dlarfg gives H = I, beta = alpha
+      A[j * n + j] = -alpha;                   // cancelled to zero: generic LAPACK outcome (see above)
+      for (int k = j + 1; k < n; ++k) A[j * n + k] = -A[j * n + k];
+      continue;
+    }
     const double norm = std::sqrt(alpha * alpha + xnorm2);
-    const double beta = (alpha >= 0.0) ? -norm : norm;
+    const double beta = std::signbit(alpha) ? norm : -norm;
     const double tau = (beta - alpha) / beta;
     const double scal = 1.0 / (alpha - beta);
     // v = [1, A[j+1:, j] * scal]; apply H = I - tau v v^T to the trailing columns
     for (int i = j + 1; i < m; ++i) A[i * n + j] *= scal;
     A[j * n + j] = beta;
     for (int k = j + 1; k < n; ++k) {
-      double w = A[j * n + k];
-      for (int i = j + 1; i < m; ++i) w += A[i * n + j] * A[i * n + k];
-      w *= tau;
+      double w = A[j * n + k], wm = fragile ? Mg[j * n + k] : 0.0;
+      for (int i = j + 1; i < m; ++i) {
+        w += A[i * n + j] * A[i * n + k];
+        if (fragile) wm += std::fabs(A[i * n + j]) * Mg[i * n + k];
+      }
+      w *= tau; wm *= std::fabs(tau);
       A[j * n + k] -= w;
-      for (int i = j + 1; i < m; ++i) A[i * n + k] -= w * A[i * n + j];
+      if (fragile) Mg[j * n + k] += wm;
+      for (int i = j + 1; i < m; ++i) {
+        const double upd = w * A[i * n + j];
+        A[i * n + k] -= upd;
+        if (upd != 0.0) touched[i * n + k] = 1;
+        if (fragile) Mg[i * n + k] += wm * std::fabs(A[i * n + j]);
+      }
     }
   }
 }
 
 // out (n x n, lower) = R^T of qr([blk0^T; blk1^T; ...]); each block is rows x n? No: each block
 // b_k is an [n x c_k] factor; the stacked matrix has sum(c_k) rows and n columns.
+thread_local long long g_fragile = 0;     // fragile columns seen by this thread (see householder_R)
+bool g_count_fragile = false;             // set per run (diagnostic; off for the timed CPU baseline)
 void qr_stack(int n, int nblk, const double* const* blk, const int* cols, double* out) {
   int m = 0;
   for (int k = 0; k < nblk; ++k) m += cols[k];
@@ -262,7 +304,7 @@ void qr_stack(int n, int nblk, const double* const* blk, const int* cols, double
       for (int i = 0; i < n; ++i) A[(size_t)(r0 + c) * n + i] = blk[k][i * cols[k] + c];  // transpose
     r0 += cols[k];
   }
-  householder_R(A.data(), m, n);
+  householder_R(A.data(), m, n, g_count_fragile ? &g_fragile : nullptr);
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) out[i * n + j] = (j <= i && j < m) ? A[(size_t)j * n + i] : 0.0;
 }
@@ -430,7 +472,7 @@ long long oracle_ekf_run(int ode_id, int variant, int nc, int n, int p, int solv
                          const unsigned char* flags, const long long* ymap, long long save_interval,
                          int guard_intended, int nthreads, double* xT, double* PT, double* nll,
                          double* out_t, double* out_x, double* out_eps, double* out_P,
-                         double* out_yhat, double* out_S, long long* fired_out) {
+                         double* out_yhat, double* out_S, long long* fired_out, long long* fragile_out) {
   Cfg c;
   c.ode = {ode_id, variant, nc, n, p};
   c.tb = make_tableau(solver_id);
@@ -439,9 +481,11 @@ long long oracle_ekf_run(int ode_id, int variant, int nc, int n, int p, int solv
   bool qany = false;
   std::vector<double> Qz(n * n, 0.0);
   if (Q_sqrt) for (int i = 0; i < n * n; ++i) { Qz[i] = Q_sqrt[i]; qany = qany || (Q_sqrt[i] >= 1e-16); }
-  std::atomic<long long> mismatch_total{0}, fired_total{0};
+  std::atomic<long long> mismatch_total{0}, fired_total{0}, fragile_total{0};
+  g_count_fragile = fragile_out != nullptr;
   auto run_one = [&](long long b) {
     g_K = n;
+    const long long fragile0 = g_fragile;
     double x[NMAX], eps[NMAX], Ps[NMAX * NMAX], yhat[NMAX], S_sqrt[NMAX * NMAX];
     for (int i = 0; i < n; ++i) { x[i] = x0[b * n + i]; eps[i] = 0.0; yhat[i] = 0.0; }
     for (int i = 0; i < n * n; ++i) Ps[i] = P0_sqrt[i];
@@ -491,6 +535,7 @@ long long oracle_ekf_run(int ode_id, int variant, int nc, int n, int p, int solv
     if (nll) nll[b] = acc;
     mismatch_total += mismatch;
     fired_total += fired;
+    fragile_total += g_fragile - fragile0;
   };
   int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
   if (nt < 1) nt = 1;
@@ -507,6 +552,7 @@ long long oracle_ekf_run(int ode_id, int variant, int nc, int n, int p, int solv
     for (auto& th : pool) th.join();
   }
   if (fired_out) *fired_out = fired_total.load();
+  if (fragile_out) *fragile_out = fragile_total.load();   // QR columns whose sign was decided by rounding
   return mismatch_total.load();
 }
 

@@ -58,7 +58,7 @@ def num_threads() -> int:
 def ekf_run(ode: str, solver: str, h: float, x0, T: int, *, t0=0.0, P0_sqrt=None, theta=None,
             Q_sqrt=None, gamma_sqrt=0.0, H=None, R_sqrt=None, ys=None, ys_per_trajectory=False,
             correct_flags=None, xy_index_map=None, cov="diagonal", scale=1.0, disable=False,
-            save_interval=0, guard="reference", nthreads=0, theta_default=None):
+            save_interval=0, guard="reference", nthreads=0, theta_default=None, count_fragile=True):
     """x0 [B, n]; theta None (-> theta_default), [p] shared or [B, p].  Returns dict like
     tests/util.run_ekf (xT, PT, nll, traj, guard_mismatch_steps, guard_fired_steps)."""
     oid, variant, nc, n, p = ode_key(ode)
@@ -84,7 +84,7 @@ def ekf_run(ode: str, solver: str, h: float, x0, T: int, *, t0=0.0, P0_sqrt=None
         Ts = T // save_interval + 1
         tr = dict(t=np.zeros(Ts), x=np.zeros((Ts, B, n)), eps=np.zeros((Ts, B, n)),
                   P=np.zeros((Ts, B, n, n)), y_hat=np.zeros((Ts, B, L)), S=np.zeros((Ts, B, L, L)))
-    fired = C.c_longlong(0)
+    fired, fragile = C.c_longlong(0), C.c_longlong(0)
     mism = lib().oracle_ekf_run(
         C.c_int(oid), C.c_int(variant), C.c_int(nc), C.c_int(n), C.c_int(p), C.c_int(SOLVER[solver]),
         C.c_double(h), C.c_int(COV[cov]), C.c_double(scale), C.c_int(int(disable)),
@@ -93,9 +93,12 @@ def ekf_run(ode: str, solver: str, h: float, x0, T: int, *, t0=0.0, P0_sqrt=None
         C.c_int(int(ys_per_trajectory)), _p(fl), _p(mp), C.c_longlong(save_interval),
         C.c_int(int(guard == "intended")), C.c_int(nthreads), _p(xT), _p(PT), _p(nll),
         _p(tr.get("t")), _p(tr.get("x")), _p(tr.get("eps")), _p(tr.get("P")),
-        _p(tr.get("y_hat")) if L else None, _p(tr.get("S")) if L else None, C.byref(fired))
+        _p(tr.get("y_hat")) if L else None, _p(tr.get("S")) if L else None, C.byref(fired),
+        C.byref(fragile) if count_fragile else None)
+    # fragile_qr_columns: Householder columns whose sign the reference's own LAPACK decides by rounding
+    # (sub-column at cancellation-noise level, see oracle/ekf_ref.cpp householder_R)
     return dict(xT=xT, PT=PT, nll=nll, traj=tr or None, guard_mismatch_steps=int(mism),
-                guard_fired_steps=int(fired.value))
+                guard_fired_steps=int(fired.value), fragile_qr_columns=int(fragile.value))
 
 
 def rk_run(ode: str, solver: str, h: float, x0, T: int, *, t0=0.0, theta=None):

@@ -128,6 +128,14 @@ int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
   const int lk = select_lk<Ode>(io);
   auto run = [&](long long b, const Segment& sg) {
     if constexpr (n <= 4) {
+      if (io.guard_mode != ODEU_GUARD_INTENDED) {          // same routing as launch_ekf
+        if (factor_fast_ok<Ode>(a, io, lk)) {
+          if (lk == 1) ekf_trajectory<Ode, Tab, KC, 1, 1>(a, b, sg);
+          else ekf_trajectory<Ode, Tab, KC, n, 1>(a, b, sg);
+        } else {
+          ekf_trajectory<Ode, Tab, KC, -1, 2>(a, b, sg);
+        }
+      } else
       if (lk == 0) ekf_trajectory<Ode, Tab, KC, 0>(a, b, sg);
       else if (lk == 1) ekf_trajectory<Ode, Tab, KC, 1>(a, b, sg);
       else if (lk == n) ekf_trajectory<Ode, Tab, KC, n>(a, b, sg);
@@ -144,12 +152,12 @@ int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
     for (long long seg = 0; seg < nseg; ++seg)
       for (long long b = 0; b < io.B; ++b) {
         Segment sg = {seg * seg_len, (seg + 1 == nseg) ? (long long)io.T : (seg + 1) * seg_len, seg == 0,
-                      seg + 1 == nseg, (double*)io.workspace};
+                      seg + 1 == nseg, (double*)io.workspace, nullptr};
         run(b, sg);
       }
     return 0;
   }
-  const Segment whole = {0, (long long)io.T, true, true, nullptr};
+  const Segment whole = {0, (long long)io.T, true, true, nullptr, nullptr};
   for (long long b = 0; b < io.B; ++b) run(b, whole);
   return 0;
 }

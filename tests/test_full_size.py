@@ -31,19 +31,24 @@ def test_config2_full_size_sample_against_oracle(system):
     flags, ymap = np.ones(T, np.uint8), np.arange(T, dtype=np.int64)
     r = ekf_run(plan, torch.as_tensor(w["x0"]).to(dev), T, t0=w["t0"], P0_sqrt=w["P0_sqrt"], H=w["H"], R_sqrt=w["R_sqrt"],
                 ys=torch.as_tensor(ys).to(dev), correct_flags=torch.as_tensor(flags).to(dev),
-                xy_index_map=torch.as_tensor(ymap).to(dev))
+                xy_index_map=torch.as_tensor(ymap).to(dev), guard="reference")
     assert torch.isfinite(r.nll).all() and torch.isfinite(r.PT).all()
     idx = np.array([0, 1, 31, 32, 63, 64, 4095, 4096, 12345, 32767, 32768, 50000, 65534, 65535])
     th = {"Lorenz": [10.0, 8.0 / 3, 28.0], "VanDerPol": [5.0]}[system]
     o = RC.ekf_run(system, "RKF45", 0.01, w["x0"][idx], T, t0=w["t0"], P0_sqrt=w["P0_sqrt"], theta=th, H=w["H"],
-                   R_sqrt=w["R_sqrt"], ys=ys, correct_flags=flags, xy_index_map=ymap, guard="intended")
-    # The oracle runs with the INTENDED zero-gain guard (what the kernels implement).  It also counts
-    # the steps on which the reference's sign-sensitive `all(S_sqrt < 1e-16)` would have fired for a
-    # healthy negative Householder factor: none for Lorenz, about a third of the steps for
-    # Van der Pol with H = I - on this workload the reference itself would silently drop those
-    # observations, which is why the comparison uses the intended semantics.
+                   R_sqrt=w["R_sqrt"], ys=ys, correct_flags=flags, xy_index_map=ymap, guard="reference")
+    # BOTH sides apply the zero-gain guard exactly as the reference writes it (`all(S_sqrt < 1e-16)` on a
+    # factor with LAPACK's Householder signs, sqrt_ekf.py:350-353): the kernels run in factor form
+    # (guard_mode reference), Oracle-B is the reference's own square-root formulation.  On Lorenz the
+    # predicate never fires; on Van der Pol with H = I it fires for healthy all-negative factors (the
+    # reference silently drops those observations) and the kernel must drop the SAME ones.
+    fired = r.guard_fired[idx].cpu().numpy()
+    assert int(fired.sum()) == o["guard_fired_steps"]
+    assert int(r.guard_mismatch[idx].sum()) == o["guard_mismatch_steps"]
     if system == "Lorenz":
-        assert o["guard_mismatch_steps"] == 0
+        assert o["guard_fired_steps"] == 0 and int(r.guard_fired.sum()) == 0
+    else:
+        assert o["guard_fired_steps"] > 0
     x, P, nll = r.xT[idx].cpu().numpy(), r.PT[idx].cpu().numpy(), r.nll[idx].cpu().numpy()
     np.testing.assert_allclose(x, o["xT"], rtol=1e-8, atol=1e-8 * np.abs(o["xT"]).max())
     np.testing.assert_allclose(P, o["PT"], rtol=1e-7, atol=1e-7 * np.abs(o["PT"]).max())

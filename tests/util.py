@@ -73,8 +73,10 @@ def make_plan(**kw):
 def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, theta_shared=None,
             Q_sqrt=None, gamma_sqrt=0.0, H=None, R_sqrt=None, ys=None, ys_per_trajectory=False,
             correct_flags=None, xy_index_map=None, save_interval=0, segmented=False, dynamic=True,
-            minimal=False, cov_scale_batch=None, nll_nan_to_num=False):
+            minimal=False, cov_scale_batch=None, nll_nan_to_num=False, guard="intended",
+            P0_sqrt_batch=None):
     """Returns dict(xT [B,n], epsT, PT [B,n,n], nll [B], tT, traj{t,x,eps,P,y_hat,S}).
+    guard != "intended" (factor form) adds PT_sqrt [B,n,n], guard_fired [B], guard_mismatch [B].
     segmented (hostemu): replay the dynamic scheduler's (block, time-segment) items sequentially."""
     x0 = _np(x0)
     B, n = x0.shape
@@ -88,11 +90,12 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
                     correct_flags=tt(correct_flags, torch.uint8),
                     xy_index_map=tt(xy_index_map, torch.int64), save_interval=save_interval,
                     dynamic=dynamic, minimal=minimal, cov_scale_batch=tt(cov_scale_batch),
-                    nll_nan_to_num=nll_nan_to_num)
+                    nll_nan_to_num=nll_nan_to_num, guard=guard, P0_sqrt_batch=tt(P0_sqrt_batch))
         torch.cuda.synchronize()
         c = lambda v: None if v is None else v.cpu().numpy()
         out = dict(xT=c(r.xT), epsT=c(r.epsT), PT=c(r.PT), nll=c(r.nll),
-                   tT=None if r.tT is None else float(r.tT), yhatT=c(r.yhatT), ST=c(r.ST))
+                   tT=None if r.tT is None else float(r.tT), yhatT=c(r.yhatT), ST=c(r.ST),
+                   PT_sqrt=c(r.PT_sqrt), guard_fired=c(r.guard_fired), guard_mismatch=c(r.guard_mismatch))
         out["traj"] = None if r.traj is None else {k: c(v) for k, v in r.traj.items()}
         return out
     assert backend == "hostemu"
@@ -107,7 +110,11 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
     L = 0
     io.B, io.T, io.t0 = B, int(T), float(t0)
     io.x0 = _p(K(np.ascontiguousarray(x0.T)))
-    if P0 is not None:
+    from ode_uncertainty_b200.engine import GUARD_MODES
+    io.guard_mode = GUARD_MODES[guard]
+    if P0_sqrt_batch is not None:
+        io.P0_sqrt_batch = _p(K(np.ascontiguousarray(_np(P0_sqrt_batch).reshape(B, n * n).T)))
+    elif P0 is not None:
         io.P0 = _p(K(np.ascontiguousarray(_np(P0).reshape(B, n * n).T)))
     else:
         P0s = np.eye(n) * 1e-12 if P0_sqrt is None else _np(P0_sqrt).reshape(n, n)
@@ -137,11 +144,14 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
         io.cov_scale_batch = _p(K(_np(cov_scale_batch).reshape(B)))
     io.nll_nan_to_num = int(bool(nll_nan_to_num))
     if segmented:
-        wsbuf = K(np.zeros((n + n * n + 1) * B + (B + 31) // 32 + 8))
+        wsbuf = K(np.zeros((n + n * n + 2) * B + (B + 31) // 32 + 8))
         io.workspace, io.workspace_bytes = _p(wsbuf), wsbuf.nbytes
     xT, epsT, PT = np.zeros((n, B)), np.zeros((n, B)), np.zeros((n * n, B))
     yT, ST = np.zeros((max(L, 1), B)), np.zeros((max(L * L, 1), B))
     nll, tT = np.zeros(B), np.zeros(1)
+    PsT, gcount = np.zeros((n * n, B)), np.zeros((2, B), dtype=np.int64)
+    if guard != "intended":
+        io.PT_sqrt, io.guard_counts = _p(PsT), _p(gcount)
     if minimal:      # only nll, xT, PT requested (lets medium systems take the cooperative kernel)
         io.xT, io.PT, io.nll = map(_p, (xT, PT, nll))
     else:
@@ -161,6 +171,8 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
         raise ValueError(f"hostemu: {emu.hostemu_last_error().decode()} ({rc})")
     out = dict(xT=xT.T.copy(), epsT=epsT.T.copy(), PT=PT.T.reshape(B, n, n).copy(), nll=nll,
                tT=float(tT[0]), yhatT=yT[:L].T.copy(), ST=ST[:L * L].T.reshape(B, L, L).copy())
+    if guard != "intended":
+        out.update(PT_sqrt=PsT.T.reshape(B, n, n).copy(), guard_fired=gcount[0].copy(), guard_mismatch=gcount[1].copy())
     out["traj"] = None
     if tr is not None:
         Ts = tr["t"].shape[0]

@@ -8,13 +8,16 @@ OBJDIR    := build/obj
 LIB       := ode_uncertainty_b200/libodeu.so
 SRCS      := $(wildcard $(CSRC)/*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
-HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/odeu.h
+DEPS      := $(OBJS:.o=.d)
 
 all: $(LIB) oracle
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+# per-object header dependencies (nvcc -MMD): a header edit rebuilds only the units that include it
+$(OBJDIR)/%.o: $(CSRC)/%.cu
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVFLAGS) $(EXTRA) -c $< -o $@
+	$(NVCC) $(NVFLAGS) $(EXTRA) -MMD -MP -MF $(OBJDIR)/$*.d -c $< -o $@
+
+-include $(DEPS)
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -cudart shared -o $@ $(OBJS)

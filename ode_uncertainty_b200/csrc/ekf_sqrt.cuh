@@ -26,18 +26,11 @@ struct DenseRows {
   ODEU_HD static constexpr bool single(int) { return false; }
 };
 
-ODEU_HD double copysign_hd(double mag, double sgn) {
-#ifdef __CUDA_ARCH__
-  return copysign(mag, sgn);
-#else
-  return std::copysign(mag, sgn);
-#endif
-}
-
 // In-place Householder triangularisation of A [MR][NC] (rows >= NC are eliminated), R only.
 // On return the upper triangle of the first NC rows holds R with dgeqr2/dlarfg signs; rinv[j] =
-// 1 / R_jj; *pivsq (optional) is multiplied by R_jj^2 for every processed column.  ncols: columns
-// actually present (run-time, <= NC).
+// 1 / R_jj.  ncols: columns actually present (run-time, <= NC).
+// Branch-free per column: a sub-column that is exactly zero (dlarfg: H = I, beta = alpha) selects
+// g = 0, so the trailing update adds zeros, instead of branching around it.
 template <int MR, int NC, class St>
 ODEU_HD void householder_R(double (&A)[MR][NC], double* rinv, int ncols = NC) {
 #pragma unroll
@@ -48,36 +41,35 @@ ODEU_HD void householder_R(double (&A)[MR][NC], double* rinv, int ncols = NC) {
       for (int i = j + 1; i < MR; ++i)
         if (St::first(i) <= j) xn2 = fma(A[i][j], A[i][j], xn2);
       const double alpha = A[j][j];
-      if (xn2 != 0.0) {
-        const double s2 = fma(alpha, alpha, xn2);
-        const double r = rsqrt(s2);
-        const double nrm = s2 * r;
-        const double beta = -copysign_hd(nrm, alpha);     // Fortran SIGN: the sign BIT of alpha
-        const double u = alpha - beta;
-        const double g = -1.0 / fma(fabs(alpha), nrm, s2);  // 1 / (beta u), no cancellation
+      const bool ident = !(xn2 != 0.0);                    // (a NaN sub-column takes the reflector path)
+      const double s2 = fma(alpha, alpha, xn2);
+      const double r = rsqrt_pos(s2);
+      const double nrm = s2 * r;
+      // Fortran SIGN: the sign BIT of alpha decides (alpha = +0 reflects to -norm)
+      const double beta = ident ? alpha : -copysign_hd(nrm, alpha);
+      const double u = alpha - beta;
+      // H = I + w w^T / (beta u), w = [u; x];  beta u = -(|alpha| nrm + s2): no cancellation
+      const double g = ident ? 0.0 : -rcp_pos(fma(fabs(alpha), nrm, s2));
 #pragma unroll
-        for (int k = j + 1; k < NC; ++k) {
-          if (k < ncols) {
-            double wa = u * A[j][k];
+      for (int k = j + 1; k < NC; ++k) {
+        if (k < ncols) {
+          double wa = u * A[j][k];
 #pragma unroll
-            for (int i = j + 1; i < MR; ++i)
-              if (St::first(i) <= j && !(St::single(i) && St::first(i) == j)) wa = fma(A[i][j], A[i][k], wa);
-            wa *= g;
-            A[j][k] = fma(wa, u, A[j][k]);
+          for (int i = j + 1; i < MR; ++i)
+            if (St::first(i) <= j && !(St::single(i) && St::first(i) == j)) wa = fma(A[i][j], A[i][k], wa);
+          wa *= g;
+          A[j][k] = fma(wa, u, A[j][k]);
 #pragma unroll
-            for (int i = j + 1; i < MR; ++i) {
-              if (St::first(i) <= j) {
-                if (St::single(i) && St::first(i) == j) A[i][k] = wa * A[i][j];
-                else A[i][k] = fma(wa, A[i][j], A[i][k]);
-              }
+          for (int i = j + 1; i < MR; ++i) {
+            if (St::first(i) <= j) {
+              if (St::single(i) && St::first(i) == j) A[i][k] = wa * A[i][j];
+              else A[i][k] = fma(wa, A[i][j], A[i][k]);
             }
           }
         }
-        A[j][j] = beta;
-        rinv[j] = -copysign_hd(r, alpha);
-      } else {
-        rinv[j] = 1.0 / alpha;   // dlarfg with xnorm == 0: H = I, R_jj = alpha (sign kept)
       }
+      A[j][j] = beta;
+      rinv[j] = ident ? copysign_hd(r, alpha) : -copysign_hd(r, alpha);   // 1 / R_jj (r = 1/|alpha| when ident)
     }
   }
 }
@@ -197,13 +189,15 @@ struct GuardCount {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Measurement update in factor form, H = [I_L 0], Ps and Rs lower-triangular on entry.
-//   S_sqrt: column j of [Ps[:L,:]^T; Rs^T] has non-zeros in rows 0..j and n..n+j only, so the
-//   reflector of column j touches row j and the rows n..n+j of the R_sqrt block: alpha_j = Ps[j][j].
+// Measurement update in factor form, H = [I_L 0], Ps lower-triangular and Rs DIAGONAL on entry
+// (every script of the reference builds R_sqrt = const_diag(L, sqrt(obs_noise_var))).
+//   S_sqrt: column j of [Ps[:L,:]^T; Rs] has non-zeros in rows 0..j and row n+j only, so the
+//   reflector of column j touches row j and the rows n..n+j of the R_sqrt block (fill-in of the
+//   earlier reflectors plus r_j): alpha_j = Ps[j][j].
 template <int n, int L>
 struct LeadSRows {
   ODEU_HD static constexpr int first(int r) { return r < L ? r : (r < n ? L : r - n); }   // L = never
-  ODEU_HD static constexpr bool single(int) { return false; }
+  ODEU_HD static constexpr bool single(int r) { return r >= n; }
 };
 
 template <int n, int L>
@@ -243,7 +237,7 @@ ODEU_HD double correct_factor_lead(const double* R, const double* Rs, const doub
 #pragma unroll
   for (int k = 0; k < L; ++k)
 #pragma unroll
-    for (int c = 0; c < L; ++c) M[n + k][c] = (c >= k) ? Rs[c * L + k] : 0.0;
+    for (int c = 0; c < L; ++c) M[n + k][c] = (c == k) ? Rs[k * L + k] : 0.0;
   householder_R<n + L, L, LeadSRows<n, L>>(M, inv);
   // S_sqrt[i][j] = M[j][i]; guards (sqrt_ekf.py:350-353: the zeros above the diagonal pass `< 1e-16`)
   bool g_ref = true, g_int = true;
@@ -328,13 +322,7 @@ ODEU_HD double correct_factor_lead(const double* R, const double* Rs, const doub
 #pragma unroll
   for (int i = 0; i < n; ++i)
 #pragma unroll
-    for (int m = 0; m < L; ++m) {
-      double s = 0.0;
-#pragma unroll
-      for (int l = 0; l < L; ++l)
-        if (l >= m) s = fma(K[i][l], Rs[l * L + m], s);
-      A2[n + m][i] = s;
-    }
+    for (int m = 0; m < L; ++m) A2[n + m][i] = K[i][m] * Rs[m * L + m];
   householder_R<n + L, n, DenseRows>(A2, rinv);
 #pragma unroll
   for (int i = 0; i < n; ++i)

@@ -211,15 +211,15 @@ int launch_ekf_variant(const EkfArgs<Ode::NX, Ode::NP>& a, const odeu_ekf_io& io
 }
 
 // Factor form (guard_mode reference): the structured variant needs H = [I_L 0] (LK > 0), the
-// NOISE_COVFN branch with a diagonal process-noise block and a lower-triangular R_sqrt; everything
-// else takes the generic factor code.
+// NOISE_COVFN branch with a diagonal process-noise block and a diagonal R_sqrt (what every script of
+// the reference builds: const_diag(L, sqrt(obs_noise_var))); everything else takes the generic code.
 template <class Ode>
 bool factor_fast_ok(const EkfArgs<Ode::NX, Ode::NP>& a, const odeu_ekf_io& io, int lk) {
   if (lk <= 0) return false;
   if (a.noise_mode != NOISE_COVFN || a.cov_fn == COV_OUTER) return false;
   for (int l = 0; l < io.L; ++l)
-    for (int m = l + 1; m < io.L; ++m)
-      if (io.R_sqrt[l * io.L + m] != 0.0) return false;
+    for (int m = 0; m < io.L; ++m)
+      if (m != l && io.R_sqrt[l * io.L + m] != 0.0) return false;
   return true;
 }
 

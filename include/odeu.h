@@ -150,6 +150,8 @@ typedef struct {
   int32_t guard_mode;        /* odeu_guard_mode */
   const double* P0_sqrt_batch; /* DEVICE [n*n][B] per-trajectory FACTOR (resume in reference mode; replaces P0) */
   double* PT_sqrt;           /* DEVICE [n*n][B] final factor with the reference's signs (reference mode), or NULL */
+  double* out_P_sqrt;        /* DEVICE [T_save][n*n][B] the factor at every saved slot = state["P_sqrt"] of the
+                                reference's traj_states, signs included (reference mode), or NULL */
   int64_t* guard_counts;     /* DEVICE [2][B] (reference mode) or NULL: measurement updates on which the guard
                                 fired (K = 0); updates on which the verbatim and the intended predicate differ */
 } odeu_ekf_io;

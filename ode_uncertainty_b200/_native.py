@@ -50,7 +50,8 @@ class EkfIO(C.Structure):
         ("tT", _dp), ("out_t", _dp), ("out_x", _dp), ("out_eps", _dp), ("out_P", _dp),
         ("out_yhat", _dp), ("out_S", _dp), ("cov_scale_batch", _dp), ("nll_nan_to_num", C.c_int32),
         ("Q_sqrt_diag_batch", _dp),
-        ("guard_mode", C.c_int32), ("P0_sqrt_batch", _dp), ("PT_sqrt", _dp), ("guard_counts", _dp),
+        ("guard_mode", C.c_int32), ("P0_sqrt_batch", _dp), ("PT_sqrt", _dp), ("out_P_sqrt", _dp),
+        ("guard_counts", _dp),
     ]
 
 

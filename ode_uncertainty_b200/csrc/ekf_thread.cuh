@@ -52,6 +52,7 @@ struct EkfArgs {
   int guard_verbatim;     // 1: `all(S_sqrt < 1e-16)` as written (sqrt_ekf.py:351); 0: intended |.|
   const double* P0f_b;    // nullable: per-trajectory factor [n*n][B] (resume)
   double* PsT;            // nullable: final factor [n*n][B]
+  double* out_Ps;         // nullable: factor per saved slot [T_save][n*n][B]
   long long* guard_counts;  // nullable: [2][B] steps the guard fired / steps the two predicates differ
   double P0f[NF];         // shared P0_sqrt
   double GQs[NF];         // gamma_sqrt * Q_sqrt
@@ -94,6 +95,16 @@ ODEU_HD void save_slot(long long slot, long long B, long long b, int L,
     for (int l = 0; l < L * L; ++l)
       if (out_S) out_S[(slot * L * L + l) * B + b] = slot > 0 ? out_S[((slot - 1) * L * L + l) * B + b] : 0.0;
   }
+}
+
+template <int n>
+ODEU_HD void save_factor_slot(long long slot, long long B, long long b, const double (*Ps)[n], double* out_Ps) {
+  if (!out_Ps) return;
+  double* p = out_Ps + slot * (n * n) * B + b;
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int j = 0; j < n; ++j) { *p = Ps[i][j]; p += B; }
 }
 
 // The whole life of trajectory `b`.  __host__ __device__ so the identical source can be
@@ -207,6 +218,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
       double Pc[n][n];
       factor_to_cov<n>(P, Pc);
       save_slot<n>(0, B, b, L, x, eps, Pc, false, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+      save_factor_slot<n>(0, B, b, P, a.out_Ps);
     } else
     save_slot<n>(0, B, b, L, x, eps, P, false, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
     if (b == 0 && a.out_t) a.out_t[0] = t;
@@ -322,6 +334,7 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
         double Pc[n][n];
         factor_to_cov<n>(P, Pc);
         save_slot<n>(slot, B, b, L, x, eps, Pc, obs_fresh, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
+        save_factor_slot<n>(slot, B, b, P, a.out_Ps);
       } else
       save_slot<n>(slot, B, b, L, x, eps, P, obs_fresh, a.out_x, a.out_eps, a.out_P, a.out_yhat, a.out_S);
       obs_fresh = false;

@@ -56,8 +56,8 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
     set_error("odeu_ekf_run: guard_mode reference resumes from the FACTOR (P0_sqrt_batch = a previous PT_sqrt), not from P0");
     return -1;
   }
-  if (!factor && (io.P0_sqrt_batch || io.PT_sqrt || io.guard_counts)) {
-    set_error("odeu_ekf_run: P0_sqrt_batch / PT_sqrt / guard_counts need guard_mode reference (factor form)");
+  if (!factor && (io.P0_sqrt_batch || io.PT_sqrt || io.out_P_sqrt || io.guard_counts)) {
+    set_error("odeu_ekf_run: P0_sqrt_batch / PT_sqrt / out_P_sqrt / guard_counts need guard_mode reference (factor form)");
     return -1;
   }
 
@@ -83,6 +83,7 @@ int fill_ekf_args(const odeu_plan& plan, const odeu_ekf_io& io, EkfArgs<Ode::NX,
   a.tT = io.tT;
   a.guard_verbatim = io.guard_mode == ODEU_GUARD_REFERENCE ? 1 : 0;
   a.P0f_b = io.P0_sqrt_batch; a.PsT = io.PT_sqrt; a.guard_counts = (long long*)io.guard_counts;
+  a.out_Ps = io.save_interval > 0 ? io.out_P_sqrt : nullptr;
   a.out_t = io.out_t; a.out_x = io.out_x; a.out_eps = io.out_eps; a.out_P = io.out_P;
   a.out_yhat = io.out_yhat; a.out_S = io.out_S;
 

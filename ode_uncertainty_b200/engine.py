@@ -225,6 +225,9 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             tr["y_hat"] = torch.empty(Ts, L, B, **f64)
         if L > 0 and "S" in save_keys:
             tr["S"] = torch.empty(Ts, L * L, B, **f64)
+        if factor and "P" in save_keys:
+            tr["P_sqrt"] = torch.empty(Ts, n * n, B, **f64)
+            io.out_P_sqrt = _dev(tr["P_sqrt"])
         io.out_t, io.out_x, io.out_eps = _dev(tr.get("t")), _dev(tr.get("x")), _dev(tr.get("eps"))
         io.out_P, io.out_yhat, io.out_S = _dev(tr.get("P")), _dev(tr.get("y_hat")), _dev(tr.get("S"))
 
@@ -239,7 +242,7 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
         for k, v in tr.items():
             if k == "t":
                 traj[k] = v
-            elif k == "P":
+            elif k in ("P", "P_sqrt"):
                 traj[k] = v.permute(0, 2, 1).reshape(v.shape[0], B, n, n)
             elif k == "S":
                 traj[k] = v.permute(0, 2, 1).reshape(v.shape[0], B, L, L)

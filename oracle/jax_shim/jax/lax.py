@@ -18,7 +18,10 @@ def scan(f, init, xs=None, length=None):
     ys = []
     for i in range(n):
         x_i = None if xs is None else pt.tree_map(lambda a: a[i], xs)
-        carry, y = f(carry, x_i)
+        # JAX hands the body a FRESH pytree of tracers every call, so `state["y"] = ...` inside the body
+        # (scripts/run_filter.py:206) never mutates the caller's initial_state nor an earlier output;
+        # rebuild the containers to keep that purity
+        carry, y = f(pt.tree_map(lambda a: a, carry), x_i)
         ys.append(y)
     if not ys or ys[0] is None:
         return carry, None

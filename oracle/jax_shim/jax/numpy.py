@@ -53,6 +53,11 @@ asarray = array
 def _shape(s):
     if isinstance(s, int):
         return (s,)
+    if callable(s):      # `x.size` is an int property in JAX and a bound method on torch tensors
+        n = 1            # (scripts/run_filter.py:75 `const_diag(x0_arr_built.size, 1e-12)`)
+        for v in s():
+            n *= int(v)
+        return (n,)
     return tuple(int(v) for v in s)
 
 

@@ -1,0 +1,268 @@
+"""The drop-in boundary, exercised end to end with the REFERENCE'S OWN scripts.
+
+CPU part (needs /root/reference, skipped where it is absent): `integration/run_filter.patch` is
+applied to a copy of the reference's `scripts/run_filter.py`; its `main()` runs twice over the jax
+shim (test infrastructure, oracle/jax_shim) - once stock (`filter_builder = SQRT_EKF`, the
+reference's own lax.scan loop) and once with `filter_builder = B200_SQRT_EKF` (integration/b200.py,
+a subclass of the reference's SQRT_EKF), whose `build_unroll` hook marshals the reference's state
+dict into ONE `odeu_ekf_run`-shaped call.  Here (no GPU) the call is served by the host-compiled
+kernel source through `reference_binding.set_runner`; the datasets the two runs write must agree.
+The stock run's datasets are committed as tests/golden/ref_main_*.npz so that the GPU part can pin
+the same marshalling + the real CUDA path on a box without the reference tree.
+
+The same for `scripts/run_parameter_estimation.py`: the hooked `nll_p` (value and forward-mode
+gradient) against the reference's `nll` / `jax.value_and_grad(nll)` fixtures."""
+import importlib.util
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import util as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("ODEU_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+CONFIGS = {
+    # name: kwargs of the reference's main() (scripts/run_filter.py:31-47) besides output / builders
+    "lorenz_rkf45_obs": dict(ode="Lorenz", solver="RKF45", h=0.01, x0="[[1.0, 1.0, 1.0]]", tN=0.3,
+                             measurement_matrix="[[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]",
+                             obs_noise_var=1e-3, obs_every=1, save_interval=3),
+    # observations every second filter step: the sign quirk of the zero-gain guard drops them
+    "vdp_rkf45_obs_every2": dict(ode="VanDerPol", solver="RKF45", h=0.01, x0="[[2.0], [10.0]]", t0=10.0, tN=10.2,
+                                 measurement_matrix="[[1.0, 0.0]]", obs_noise_var=1e-3, obs_every=2, save_interval=1),
+    "lv_dopri65_predict": dict(ode="LotkaVolterra", solver="Dopri65", h=0.05, x0="[[1.0, 1.0]]", tN=1.0,
+                               measurement_matrix=None, obs_noise_var=1e-3, obs_every=0, save_interval=1),
+}
+
+
+def _observations(cfg):
+    """(t, x) datasets of an observation file like scripts/run_ode_solver.py writes them."""
+    from oracle import ref_cpp as RC
+    th = {"Lorenz": [10.0, 8.0 / 3, 28.0], "VanDerPol": [5.0], "LotkaVolterra": [1.5, 1.0, 3.0, 1.0]}[cfg["ode"]]
+    t0 = cfg.get("t0", 0.0)
+    T = int(np.ceil((cfg["tN"] - t0) / cfg["h"]))
+    x0 = np.array(eval(cfg["x0"]), dtype=np.float64)
+    xs, _ = RC.rk_run(cfg["ode"], cfg["solver"], cfg["h"], x0.reshape(-1), T, t0=t0, theta=th)
+    k = cfg["obs_every"]
+    idx = np.arange(k, T + 1, k)
+    rng = np.random.default_rng(11)
+    ts = t0 + cfg["h"] * idx
+    return ts, (xs[idx] + rng.normal(0, cfg["obs_noise_var"] ** 0.5, xs[idx].shape)).reshape((len(idx),) + x0.shape)
+
+
+def _hostemu_runner(pk, x0, T, *, save_interval, guard, **kw):
+    from ode_uncertainty_b200 import Plan
+    return U.run_ekf("hostemu", Plan(**pk), x0, T, t0=kw["t0"], P0_sqrt=kw["P0_sqrt"], theta_shared=kw.get("theta_shared"),
+                     Q_sqrt=kw.get("Q_sqrt"), gamma_sqrt=kw.get("gamma_sqrt", 0.0), H=kw.get("H"), R_sqrt=kw.get("R_sqrt"),
+                     ys=kw.get("ys"), correct_flags=kw.get("correct_flags"), xy_index_map=kw.get("xy_index_map"),
+                     save_interval=save_interval, guard=guard)
+
+
+@pytest.fixture(scope="module")
+def reference_env(tmp_path_factory):
+    if not os.path.isdir(os.path.join(REF, "scripts")):
+        pytest.skip("reference tree absent (GPU box): the committed fixtures stand in")
+    shim = os.path.join(ROOT, "oracle", "jax_shim")
+    saved = list(sys.path)
+    sys.path[:0] = [shim, os.path.join(shim, "stubs"), REF]
+    work = tmp_path_factory.mktemp("refscripts")
+    mods = {}
+    for script, patch in (("run_filter", "run_filter.patch"), ("run_parameter_estimation", "run_parameter_estimation.patch")):
+        dst = work / f"{script}_patched.py"
+        shutil.copy(os.path.join(REF, "scripts", f"{script}.py"), dst)
+        subprocess.check_call(["patch", "-s", str(dst), os.path.join(ROOT, "integration", patch)])
+        for tag, path in (("stock", os.path.join(REF, "scripts", f"{script}.py")), ("patched", str(dst))):
+            spec = importlib.util.spec_from_file_location(f"ref_{script}_{tag}", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mods[(script, tag)] = mod
+    spec = importlib.util.spec_from_file_location("src.filters.b200", os.path.join(ROOT, "integration", "b200.py"))
+    b200 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b200)
+    yield dict(mods=mods, b200=b200, work=work)
+    sys.path[:] = saved
+
+
+def _run_main(env, tag, name, filter_cls, out):
+    import h5py                      # the npz-backed stub
+    import src.ode as ref_ode
+    import src.solvers as ref_solvers
+    cfg = CONFIGS[name]
+    main = env["mods"][("run_filter", tag)].main
+    y_path = None
+    if cfg["obs_every"]:
+        ts, xs = _observations(cfg)
+        y_path = str(env["work"] / f"{name}_obs.h5")
+        with h5py.File(y_path, "w") as f:
+            f.create_dataset("t", data=ts)
+            f.create_dataset("x", data=xs)
+    main(output=str(out), filter_builder=filter_cls(), solver_builder=getattr(ref_solvers, cfg["solver"])(step_size=cfg["h"]),
+         ode_builder=getattr(ref_ode, cfg["ode"])(), x0=cfg["x0"], t0=cfg.get("t0", 0.0), tN=cfg["tN"], y_path=y_path,
+         measurement_matrix=cfg["measurement_matrix"], obs_noise_var=cfg["obs_noise_var"], save_interval=cfg["save_interval"],
+         disable_pbar=True)
+    with np.load(str(out)) as f:
+        return {k: f[k] for k in f.files}
+
+
+def _compare_datasets(got, ref, eps_in_P=True):
+    """`got` from the B200 hook, `ref` from the reference's own loop: same keys, shapes, values."""
+    assert set(got) == set(ref), (sorted(got), sorted(ref))
+    for k in ref:
+        assert got[k].shape == ref[k].shape, (k, got[k].shape, ref[k].shape)
+        assert got[k].dtype == ref[k].dtype, (k, got[k].dtype, ref[k].dtype)
+    np.testing.assert_array_equal(got["t"], ref["t"])
+    for k in ("Q_sqrt", "gamma_sqrt", "R_sqrt", "y"):
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    sc = lambda a: max(np.abs(a).max(), 1e-300)
+    assert np.abs(got["x"] - ref["x"]).max() <= 1e-10 * sc(ref["x"])
+    ulp = np.spacing(np.abs(ref["x"]).max())
+    assert np.abs(got["eps"] - ref["eps"]).max() <= 16 * ulp + 1e-9 * sc(ref["eps"])
+    # the factor itself, Householder signs included (guard mode "reference" returns it per saved slot)
+    tolP = 5e-6 if eps_in_P else 1e-9
+    assert np.abs(got["P_sqrt"] - ref["P_sqrt"]).max() <= tolP * sc(ref["P_sqrt"]), "P_sqrt (signed factor)"
+    if ref["y_hat"].size:
+        assert np.abs(got["y_hat"] - ref["y_hat"]).max() <= 1e-10 * sc(ref["y_hat"])
+        S = lambda d: np.einsum("...ij,...kj->...ik", d["S_sqrt"], d["S_sqrt"])
+        assert np.abs(S(got) - S(ref)).max() <= tolP * sc(S(ref))
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_reference_main_with_b200_filter_builder_matches_stock_run(reference_env, name):
+    from ode_uncertainty_b200 import reference_binding as rb
+    env = reference_env
+    from src.filters import SQRT_EKF
+    stock = _run_main(env, "stock", name, SQRT_EKF, env["work"] / f"{name}_stock.h5")
+    rb.set_runner(_hostemu_runner)
+    try:
+        hooked = _run_main(env, "patched", name, env["b200"].B200_SQRT_EKF, env["work"] / f"{name}_b200.h5")
+    finally:
+        rb.set_runner(None)
+    _compare_datasets(hooked, stock)
+    # keep the committed fixture in step with what the reference computes (regenerate: ODEU_WRITE_GOLDEN=1)
+    gp = os.path.join(GOLD, f"ref_main_{name}.npz")
+    if os.environ.get("ODEU_WRITE_GOLDEN"):
+        np.savez_compressed(gp, **stock)
+    with np.load(gp) as f:
+        for k in stock:
+            np.testing.assert_allclose(f[k], stock[k], rtol=1e-12, atol=1e-300, err_msg=f"stale fixture {gp}:{k}")
+
+
+def test_b200_subclass_passes_the_scripts_type_annotation(reference_env):
+    from src.filters.filter import FilterBuilder
+    from src.filters.sqrt_ekf import SQRT_EKF
+    fb = reference_env["b200"].B200_SQRT_EKF(disable_cov_update=True)
+    assert isinstance(fb, SQRT_EKF) and isinstance(fb, FilterBuilder) and fb.disable_cov_update
+    with pytest.raises(RuntimeError, match="no CPU fallback"):       # no GPU here, no silent fallback
+        _run_main(reference_env, "patched", "lv_dopri65_predict", reference_env["b200"].B200_SQRT_EKF,
+                  reference_env["work"] / "never.h5")
+
+
+# ---- stand-ins with the reference's class NAMES: what reference_binding duck-types on ----------------
+def _standins(cfg, guard="auto"):
+    mk = lambda name, **attrs: type(name, (), attrs)()
+    params = {"Lorenz": dict(sigma=10.0, beta=8.0 / 3, rho=28.0), "VanDerPol": dict(damping=5.0),
+              "LotkaVolterra": dict(alpha=1.5, beta=1.0, gamma=3.0, delta=1.0)}[cfg["ode"]]
+    ob = mk(cfg["ode"], params={k: np.array(v) for k, v in params.items()})
+    sb = mk(cfg["solver"], h=cfg["h"])
+    fb = mk("B200_SQRT_EKF", cov_update_fn_builder=mk("DiagonalCovarianceUpdate", scale=1.0),
+            static_cov_update_fn_builder=mk("StaticDiagonalCovarianceUpdate", scale=1.0), disable_cov_update=False)
+    return fb, sb, ob
+
+
+def _state_from_fixture(ref, cfg):
+    """initial_state as SQRT_EKF.init_state builds it (slot 0 of the stock run's datasets)."""
+    return {k: ref[k][0] for k in ("t", "x", "eps", "P_sqrt", "Q_sqrt", "gamma_sqrt", "y", "y_hat", "R_sqrt", "S_sqrt")}
+
+
+def _schedule(cfg):
+    from ode_uncertainty_b200.runners import observation_schedule
+    t0 = cfg.get("t0", 0.0)
+    T = int(np.ceil((cfg["tN"] - t0) / cfg["h"]))
+    if not cfg["obs_every"]:
+        return T, np.eye(1), np.zeros((1, 0)), np.zeros(T, bool), np.zeros(T, np.int64)
+    ts, xs = _observations(cfg)
+    _, flags, ymap = observation_schedule(t0, cfg["tN"], cfg["h"], ts)
+    H = np.array(eval(cfg["measurement_matrix"]), dtype=np.float64)
+    return T, H, np.einsum("ij,tj->ti", H, xs.reshape(-1, H.shape[1])), flags, ymap
+
+
+@pytest.mark.parametrize("backend", ["hostemu", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_binding_reproduces_the_reference_mains_datasets(name, backend):
+    """reference_binding.unroll (the body of B200_SQRT_EKF.build_unroll) on the committed datasets of
+    the reference's stock main(): runs without the reference tree; backend gpu = the real CUDA path."""
+    from ode_uncertainty_b200 import reference_binding as rb
+    cfg = CONFIGS[name]
+    with np.load(os.path.join(GOLD, f"ref_main_{name}.npz")) as f:
+        ref_strided = {k: f[k] for k in f.files}
+    fb, sb, ob = _standins(cfg)
+    T, H, ys, flags, ymap = _schedule(cfg)
+    st = _state_from_fixture(ref_strided, cfg)
+    rb.set_runner(_hostemu_runner if backend == "hostemu" else None)
+    try:
+        out = rb.unroll(fb, sb, ob, False, H, st, ys, flags, ymap, T, cfg["save_interval"])
+    finally:
+        rb.set_runner(None)
+    _compare_datasets({k: out[k] for k in ref_strided}, ref_strided)
+
+
+# ---- run_parameter_estimation.py hook: nll_p value + forward-mode gradient ---------------------------
+def _hostemu_grad_runner(pk, x0, T, grad_idx, *, x0_tangent=None, sensitivity=False, **kw):
+    from ode_uncertainty_b200 import Plan
+    assert not sensitivity
+    return U.run_grad("hostemu", Plan(**pk), x0, T, grad_idx, t0=kw["t0"], P0_sqrt=kw["P0_sqrt"], theta=kw["theta"],
+                      Q_sqrt=kw["Q_sqrt"], gamma_sqrt=kw["gamma_sqrt"], H=kw["H"], R_sqrt=kw["R_sqrt"], ys=kw["ys"],
+                      correct_flags=kw["correct_flags"], xy_index_map=kw["xy_index_map"], x0_tangent=x0_tangent)
+
+
+NLLP_CASES = {"lv_rkf45_temper_q_only": ("LotkaVolterra", None), "hh_r1_rkf45_temper": ("HodgkinHuxley", "reduced-1")}
+
+
+@pytest.mark.parametrize("backend", ["hostemu", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("name", list(NLLP_CASES))
+def test_nll_p_hook_value_and_gradient_match_the_reference(name, backend):
+    """`B200_SQRT_EKF.build_nll_p` (body: reference_binding.NllP) called exactly like the reference's
+    jitted `nll_p` / like jaxopt calls `fun(params, **kwargs)`, against the reference's own nll() and
+    jax.value_and_grad(nll) (tests/golden/ref_*.npz, produced by oracle/make_golden_ref.py)."""
+    from ode_uncertainty_b200 import ode as O
+    from ode_uncertainty_b200 import reference_binding as rb
+    spec = cases.CASES[name]
+    m = cases.materialize(spec)
+    ref = dict(np.load(os.path.join(GOLD, f"ref_{name}.npz")))
+    cls, model = NLLP_CASES[name]
+    ours = getattr(O, cls)() if model is None else getattr(O, cls)(model=model)
+    mk = lambda nm, **attrs: type(nm, (), attrs)()
+    ob = mk(cls, params={k: np.asarray(v) for k, v in ours.params.items()}, model=model,
+            build_initial_value=ours.build_initial_value)
+    sb = mk(spec["solver"], h=m["h"])
+    fb = mk("B200_SQRT_EKF", cov_update_fn_builder=mk("DiagonalCovarianceUpdate", scale=m["scale"]),
+            static_cov_update_fn_builder=mk("StaticDiagonalCovarianceUpdate", scale=1.0), disable_cov_update=m["disable"])
+    keys = list(ob.params)
+    lo = {k: np.minimum(0.5 * ob.params[k], 2.0 * ob.params[k]).reshape(-1) for k in keys}
+    hi = {k: np.maximum(0.5 * ob.params[k], 2.0 * ob.params[k]).reshape(-1) for k in keys}
+    pn = {k: (ob.params[k].reshape(-1) - lo[k]) / (hi[k] - lo[k]) for k in keys}
+    opt = {k: np.full(lo[k].shape, True) for k in keys}
+    idx = np.arange(sum(v.size for v in lo.values()))
+    n = m["n"]
+    st = dict(t=np.array([m["t0"]]), x=m["x0"].numpy()[None], P_sqrt=m["P0s"].numpy()[None], Q_sqrt=m["Q"].numpy(),
+              gamma_sqrt=np.array(m["gamma"] ** 0.5), R_sqrt=m["Rs"].numpy())
+    nll_p = rb.NllP(fb, sb, ob, m["T"], False, False)
+    rb.set_grad_runner(_hostemu_grad_runner if backend == "hostemu" else None)
+    try:
+        val = nll_p(pn, st, m["x0"].numpy(), m["H"].numpy(), m["ys"].numpy(), m["flags"], m["ymap"], lo, hi, opt, idx, ob.params)
+        val2, g = nll_p.value_and_grad(pn, initial_state=st, x0=m["x0"].numpy(), measurement_matrix=m["H"].numpy(),
+                                       ys=m["ys"].numpy(), correct_flags=m["flags"], xy_index_map=m["ymap"], params_min=lo,
+                                       params_max=hi, params_optimized=opt, params_optimized_indices=idx,
+                                       params_default=ob.params)
+    finally:
+        rb.set_grad_runner(None)
+    assert val == val2 and abs(val - float(ref["nll_fn"])) <= 1e-9 * abs(float(ref["nll_fn"]))
+    assert set(g) == set(pn) and all(g[k].shape == pn[k].shape for k in pn)
+    gflat = np.concatenate([g[k].reshape(-1) for k in sorted(g)])          # ravel_pytree order
+    np.testing.assert_allclose(gflat, ref["grad_norm"], rtol=1e-6, atol=1e-6 * np.abs(ref["grad_norm"]).max())

@@ -165,6 +165,9 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
         io.out_t, io.out_x, io.out_eps, io.out_P = map(_p, (tr["t"], tr["x"], tr["eps"], tr["P"]))
         if L > 0:
             io.out_yhat, io.out_S = _p(tr["y_hat"]), _p(tr["S"])
+        if guard != "intended":
+            tr["P_sqrt"] = np.zeros((Ts, n * n, B))
+            io.out_P_sqrt = _p(tr["P_sqrt"])
     th = (C.c_double * plan.p)(*plan.default_params)
     rc = emu.hostemu_ekf_run(C.byref(plan.desc), th, plan.p, C.byref(io))
     if rc != 0:
@@ -180,6 +183,8 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
                            P=tr["P"].transpose(0, 2, 1).reshape(Ts, B, n, n),
                            y_hat=tr["y_hat"][:, :L].transpose(0, 2, 1),
                            S=tr["S"][:, :L * L].transpose(0, 2, 1).reshape(Ts, B, L, L))
+        if "P_sqrt" in tr:
+            out["traj"]["P_sqrt"] = tr["P_sqrt"].transpose(0, 2, 1).reshape(Ts, B, n, n)
     return out
 
 

@@ -243,6 +243,88 @@ def _other_configs(dev, timed):
     return out
 
 
+def _scale_extras(dev, world, rank):
+    """The collective-bearing configs under the driver's clock at EVERY world size:
+    C3 loss + gradient with the all-reduce of the batch loss/gradient (weak scaling: 4,096 parameter sets
+    per GPU) and C4, the 1M-particle bootstrap filter sharded over the ranks (strong scaling) with its
+    global weight normalisation and resampling exchange.  Timed on the device, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from ode_uncertainty_b200 import Plan, _native as N, ekf_grad_run, pf_run, runners
+    from ode_uncertainty_b200 import distributed as D
+    from ode_uncertainty_b200 import ode as O
+    from ode_uncertainty_b200.particle_filter_ext import bootstrap_filter
+
+    def timed(fn, reps=2):
+        best, out = 1e30, None
+        for _ in range(reps + 1):                      # first repetition = warm-up
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            best = min(best, float(tt.item()))
+        return best, out
+
+    out = {}
+    # ---- C3: loss + forward-mode gradient over 12 parameters, batch loss/gradient summed over all ranks
+    ob = O.MultiCompartmentHodgkinHuxley(model="reduced-1", num_compartments=2)
+    plan = Plan(N.ODE_MULTI_HH, N.SOLVER_RKF45, 0.01, ode_variant=1, num_compartments=2, disable_cov_update=True)
+    B3, T3 = 4096, 200
+    th0 = ob.flat_params(ob.params)
+    x0 = ob.build_initial_value(np.array([[-70.0, -70.0]]), ob.params).reshape(-1)
+    xs = runners.solve_trajectory(plan, x0, T3, theta_shared=th0, device=dev)
+    ys = xs[1:][:, [0, 7]] + np.random.default_rng(621).normal(0, 0.1 ** 0.5, (T3, 2))
+    off, o = {}, 0
+    for k in ob.params:
+        off[k] = o
+        o += ob.params[k].size
+    opt = ["g_Na", "g_K", "g_leak", "V_T", "g_M", "g_L"]
+    idx = np.concatenate([np.arange(off[k], off[k] + 2) for k in opt])
+    rng = np.random.default_rng(7 + 1000 * rank)
+    theta = np.repeat(th0[None, :], B3, 0)
+    for k in opt:
+        sl = slice(off[k], off[k] + 2)
+        theta[:, sl] = th0[sl] + rng.uniform(-3, 3, (B3, 2)) if k == "V_T" else th0[sl] * (1 + 0.2 * rng.uniform(-1, 1, (B3, 2)))
+    H = np.zeros((2, 14)); H[0, 0] = 1; H[1, 7] = 1
+    kw = dict(P0_sqrt=np.eye(14) * 1e-12, theta=torch.from_numpy(theta).to(dev), Q_sqrt=np.eye(14), gamma_sqrt=0.1, H=H,
+              R_sqrt=np.eye(2) * 0.1 ** 0.5, ys=torch.from_numpy(ys).to(dev),
+              correct_flags=torch.ones(T3, dtype=torch.uint8, device=dev), xy_index_map=torch.arange(T3, device=dev))
+    x0b = torch.from_numpy(np.repeat(x0[None, :], B3, 0)).to(dev)
+
+    def c3():
+        nll, g = ekf_grad_run(plan, x0b, T3, idx, **kw)
+        msg = torch.cat([nll.sum().reshape(1), g.sum(0)])          # 1 + 12 doubles
+        if world > 1:
+            dist.all_reduce(msg)                                    # NCCL, same stream
+        return msg
+
+    t3, msg = timed(c3)
+    out["c3_scale"] = {"param_set_steps_per_s": world * B3 * T3 / t3, "n_gpus": world, "scaling": "weak",
+                       "sample": f"B={B3} parameter sets per GPU x T={T3}, p=12, all-reduce of 13 doubles per evaluation",
+                       "ms": 1e3 * t3, "finite": bool(torch.isfinite(msg).all())}
+    # ---- C4: 1M particles sharded over the ranks (strong scaling); bootstrap filter with a resampling
+    # exchange at every observation (ess_frac = 2 forces it: with solver-error-sized noise the ESS test never fires)
+    planp = Plan(N.ODE_LORENZ, N.SOLVER_RKF45, 0.01)
+    M4, T4, every = 1_000_000, 1000, 10
+    if M4 % world == 0:
+        lo, hi = D.shard_bounds(M4, rank, world)
+        tp, _ = timed(lambda: pf_run(planp, hi - lo, T4, x0_shared=[1.0, 1.0, 1.0], seed=7, particle_offset=lo, device=dev))
+        xs4 = runners.solve_trajectory(planp, [1.0, 1.0, 1.0], T4, device=dev)
+        ys4 = xs4[every::every] + np.random.default_rng(8).normal(0.0, 0.1, xs4[every::every].shape)
+        tb, res = timed(lambda: bootstrap_filter(planp, M4, T4, ys4, every, np.eye(3), np.eye(3) * 1e-2,
+                                                 x0_shared=[1.0, 1.0, 1.0], seed=7, device=dev, ess_frac=2.0))
+        out["c4_scale"] = {"predict_particle_steps_per_s": M4 * T4 / tp, "bootstrap_particle_steps_per_s": M4 * T4 / tb,
+                           "bootstrap_over_predict_time": tb / tp, "n_gpus": world, "scaling": "strong",
+                           "sample": f"M={M4} particles over {world} GPU(s) x T={T4} (config: T=5000), weights every {every} steps, "
+                                     f"{len(res['resampled'])} resampling exchanges (forced), 2 all-gathers per observation, no host read",
+                           "predict_ms": 1e3 * tp, "bootstrap_ms": 1e3 * tb}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -453,6 +535,16 @@ def main():
                 extras.update(_other_configs(dev, timed))
             except Exception as exc:  # never lose the headline line to an extra
                 extras["other_configs_error"] = f"{type(exc).__name__}: {exc}"
+
+    # ---- collective-bearing configs at every world size (all ranks take part)
+    if B == 65536 and T == 10000:
+        try:
+            sc = _scale_extras(dev, world, rank)
+            if rank == 0:
+                extras.update(sc)
+        except Exception as exc:
+            if rank == 0:
+                extras["scale_extras_error"] = f"{type(exc).__name__}: {exc}"
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample
     cpu = None

@@ -174,6 +174,29 @@ int odeu_pf_weight_update(int64_t M, int32_t n, int32_t L, const double* x_dev, 
                           const double* H_host, const double* R_host, double* logw_dev,
                           void* cuda_stream);
 
+/* EXTENSION (bootstrap filter, BASELINE config 4; no reference counterpart): the global steps without a
+ * host round trip.  Per observation, on one stream:
+ *   odeu_pf_weight_reduce  logw += log N(y; H x, R) fused with this rank's triple
+ *                          (max logw, sum exp(logw - max), sum exp(2 (logw - max))) -> triple_out [3]
+ *   (caller: one all-gather of the G triples - NCCL - on the same stream)
+ *   odeu_pf_normalize      lse over the G triples; logw -= lse; stats = {lse, ESS, resample flag, running
+ *                          log-likelihood (accumulated)} as DEVICE scalars; pack [M][n+1] rows (x, w)
+ *   (caller: one all-gather of the packed rows and an inclusive cumulative sum of the weights)
+ *   odeu_pf_resample       systematic resampling (slot j of the GLOBAL ensemble takes the particle whose
+ *                          CDF interval contains (j + u0) / M_total), predicated on stats[2]; writes the
+ *                          [n][M] layout odeu_pf_run reads and resets logw to -log M_total
+ * scratch: odeu_pf_reduce_scratch_bytes(M) bytes, zeroed once by the caller. */
+int64_t odeu_pf_reduce_scratch_bytes(int64_t M);
+int odeu_pf_weight_reduce(int64_t M, int32_t n, int32_t L, const double* x_dev, const double* y_host,
+                          const double* H_host, const double* R_host, double* logw_dev,
+                          double* triple_out_dev, void* scratch_dev, void* cuda_stream);
+int odeu_pf_normalize(int64_t M, int64_t M_total, int32_t n, int32_t G, const double* triples_dev,
+                      const double* x_dev, double* logw_dev, double* pack_dev, double* stats_dev,
+                      double* ess_hist_dev, double* flag_hist_dev, double ess_frac, void* cuda_stream);
+int odeu_pf_resample(int64_t M, int64_t M_total, int64_t slot_lo, int32_t n, double u0,
+                     const double* stats_dev, const double* cdf_dev, const double* pack_dev,
+                     double* x_new_dev, double* logw_dev, void* cuda_stream);
+
 /* NLL and its parameter gradient for B parameter sets: replaces jax.value_and_grad(nll) as the
  * optimiser calls it (scripts/run_parameter_estimation.py:599, nll :685-796).  Forward-mode
  * tangents over the requested parameters (at most 32), fused with the filter loop.  Uses from

@@ -24,6 +24,7 @@ SYMBOLS = (
     "odeu_launch_count", "odeu_last_error", "odeu_bench_dfma", "odeu_ode_rhs",
     "odeu_ekf_grad_run", "odeu_ekf_workspace_bytes", "odeu_pf_weight_update",
     "odeu_ekf_dense_run", "odeu_ekf_dense_workspace_bytes", "odeu_param_sensitivity",
+    "odeu_pf_reduce_scratch_bytes", "odeu_pf_weight_reduce", "odeu_pf_normalize", "odeu_pf_resample",
 )
 
 
@@ -120,6 +121,14 @@ def lib() -> C.CDLL:
     L.odeu_pf_weight_update.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.odeu_pf_weight_update.restype = C.c_int
+    L.odeu_pf_reduce_scratch_bytes.argtypes = [C.c_int64]
+    L.odeu_pf_reduce_scratch_bytes.restype = C.c_int64
+    L.odeu_pf_weight_reduce.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 8
+    L.odeu_pf_weight_reduce.restype = C.c_int
+    L.odeu_pf_normalize.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 7 + [C.c_double, C.c_void_p]
+    L.odeu_pf_normalize.restype = C.c_int
+    L.odeu_pf_resample.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_double] + [C.c_void_p] * 6
+    L.odeu_pf_resample.restype = C.c_int
     L.odeu_ekf_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     L.odeu_ekf_workspace_bytes.restype = C.c_int64
     L.odeu_ekf_dense_workspace_bytes.argtypes = [C.c_void_p, C.c_int64]

@@ -107,10 +107,17 @@ def _u0(seed: int, event: int) -> float:
 
 def bootstrap_filter(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R, *, x0_shared,
                      t0: float = 0.0, seed: int = 7, ess_frac: float = 0.5, theta_shared=None,
-                     device="cuda") -> Dict[str, torch.Tensor]:
+                     device="cuda", fused: bool = True) -> Dict[str, torch.Tensor]:
     """Bootstrap particle filter: `obs_every` prediction steps between observations `ys[k]`.
     Returns local particles, normalised log-weights, per-observation ESS and the resample events,
-    plus the log marginal likelihood estimate."""
+    plus the log marginal likelihood estimate.
+
+    fused (default): the sync-free device path (`_bootstrap_fused`: three CUDA kernels and two
+    all-gathers per observation, no host read until the end); fused=False keeps the round-1 eager
+    formulation (host-synchronised all-to-all), used as the cross-check in tests."""
+    if fused:
+        return _bootstrap_fused(plan, M_total, T, ys, obs_every, H, R, x0_shared=x0_shared, t0=t0, seed=seed,
+                                ess_frac=ess_frac, theta_shared=theta_shared, device=device)
     rank, ws = D.world()
     lo, hi = D.shard_bounds(M_total, rank, ws)
     M = hi - lo
@@ -137,3 +144,69 @@ def bootstrap_filter(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R,
             resampled.append(k)
     return {"x": x, "logw": logw, "ess": torch.tensor(ess_hist), "resampled": resampled,
             "loglik": loglik, "t": t}
+
+
+def _bootstrap_fused(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R, *, x0_shared, t0, seed, ess_frac,
+                     theta_shared, device) -> Dict[str, torch.Tensor]:
+    """Device-resident bootstrap filter.  Per observation, all on torch's current stream:
+    odeu_pf_run (obs_every steps) -> odeu_pf_weight_reduce -> all-gather of G x 3 doubles ->
+    odeu_pf_normalize -> all-gather of the packed (x, w) rows -> cumsum -> odeu_pf_resample.
+    The ESS test, the resampling decision and the log-likelihood stay on the device; the host reads
+    them once after the last observation.  Every rank resamples its own global slots from the SAME
+    gathered CDF, so the result does not depend on the number of ranks.  Needs M_total % world == 0."""
+    rank, ws = D.world()
+    if M_total % ws:
+        raise ValueError(f"the fused bootstrap filter shards evenly: M_total={M_total} is not a multiple of {ws} ranks")
+    M = M_total // ws
+    lo = rank * M
+    dev = torch.device(device)
+    n = plan.n
+    f64 = dict(dtype=torch.float64, device=dev)
+    Hh = np.ascontiguousarray(np.asarray(H, dtype=np.float64))
+    L = Hh.shape[0]
+    Rh = np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(L, L))
+    ysh = np.ascontiguousarray(np.asarray(ys, dtype=np.float64))
+    n_obs = T // obs_every
+    lib = N.lib()
+    xk = torch.as_tensor(np.asarray(x0_shared, dtype=np.float64).reshape(n, 1)).to(dev).repeat(1, M).contiguous()  # [n][M]
+    logw = torch.full((M,), -math.log(M_total), **f64)
+    triple = torch.zeros(3, **f64)
+    triples = torch.zeros(ws, 3, **f64)
+    pack = torch.empty(M, n + 1, **f64)
+    pack_all = pack if ws == 1 else torch.empty(M_total, n + 1, **f64)
+    stats = torch.zeros(4, **f64)
+    ess_hist = torch.zeros(max(n_obs, 1), **f64)
+    flag_hist = torch.zeros(max(n_obs, 1), **f64)
+    scratch = torch.zeros(int(lib.odeu_pf_reduce_scratch_bytes(M)), dtype=torch.uint8, device=dev)
+    p = lambda t_: C.c_void_p(t_.data_ptr())
+    hp = lambda a_: a_.ctypes.data_as(C.c_void_p)
+    t = float(t0)
+    h = plan.step_size
+    for k in range(n_obs):
+        r = pf_run(plan, M, obs_every, x0=xk.t(), t0=t, theta_shared=theta_shared, seed=seed,
+                   particle_offset=lo, step_offset=k * obs_every)
+        xk = r.xT.t()                                   # the kernel's own [n][M] buffer, no copy
+        for _ in range(obs_every):
+            t = t + h                                   # the kernel accumulates t the same way (rksolver.py:145)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        yk = np.ascontiguousarray(ysh[k])
+        with torch.cuda.device(dev):
+            N.check(lib.odeu_pf_weight_reduce(M, n, L, p(xk), hp(yk), hp(Hh), hp(Rh), p(logw), p(triple), p(scratch), st),
+                    "odeu_pf_weight_reduce")
+            if ws > 1:
+                dist.all_gather_into_tensor(triples, triple.reshape(1, 3))
+            else:
+                triples = triple.reshape(1, 3)
+            N.check(lib.odeu_pf_normalize(M, M_total, n, ws, p(triples), p(xk), p(logw), p(pack), p(stats),
+                                          C.c_void_p(ess_hist.data_ptr() + 8 * k), C.c_void_p(flag_hist.data_ptr() + 8 * k),
+                                          float(ess_frac), st), "odeu_pf_normalize")
+            if ws > 1:
+                dist.all_gather_into_tensor(pack_all, pack)
+            cdf = torch.cumsum(pack_all[:, n], 0)
+            x_new = xk.clone()                          # kept when the device-side decision says "no resampling"
+            N.check(lib.odeu_pf_resample(M, M_total, lo, n, _u0(seed, k), p(stats), p(cdf), p(pack_all), p(x_new), p(logw), st),
+                    "odeu_pf_resample")
+        xk = x_new
+    flags = flag_hist[:n_obs].cpu().numpy()             # the only device-to-host reads of the run
+    return {"x": xk.t(), "logw": logw, "ess": ess_hist[:n_obs].cpu(), "resampled": [int(k) for k in np.nonzero(flags)[0]],
+            "loglik": float(stats[3]), "t": t}

@@ -517,6 +517,31 @@ def main():
         bytes_str = B * (Ts + 1) * (3 + 3 + 9) * 8
         extras["lorenz_streaming_save_every_step"] = {"traj_steps_per_s": B * Ts / t_str,
                                                       "hbm_write_GBps": bytes_str / t_str / 1e9}
+        # SURVEY 8(d) C2(2b) as specified: PER-TRAJECTORY observations y_t = x_t^(2a) + N(0, 1e-3) of each
+        # trajectory's own prediction-only solution, P0_sqrt = 1e-12 I; the 15.7 GB observation stream
+        # ys [T][L][B] is read once per launch (coalesced 256-byte rows per warp and component)
+        if B == 65536 and T == 10000:
+            try:
+                pred = ekf_run(plans["Lorenz"], w["x0_dev"], T, P0_sqrt=np.eye(3) * 1e-12, save_interval=1, save_keys=("x",),
+                               want_final=False)
+                ys_pt = pred.traj["x"][1:]                                   # [T, B, n] view of the kernel's [T][n][B]
+                del pred
+                gen = torch.Generator(device=dev); gen.manual_seed(8)
+                ys_pt = ys_pt + (1e-3 ** 0.5) * torch.randn(ys_pt.shape, generator=gen, dtype=torch.float64, device=dev)
+                kw_pt = dict(t0=w["t0"], P0_sqrt=np.eye(3) * 1e-12, H=w["H"], R_sqrt=w["R_sqrt"], ys=ys_pt, ys_per_trajectory=True,
+                             correct_flags=w["flags"], xy_index_map=w["ymap"], guard=args.guard)
+                t_pt = timed(lambda: ekf_run(plans["Lorenz"], w["x0_dev"], T, **kw_pt), reps=2)
+                r_pt = ekf_run(plans["Lorenz"], w["x0_dev"], T, **kw_pt)
+                extras["c2_per_trajectory_obs"] = {
+                    "lorenz_traj_steps_per_s": B * T / t_pt, "ms": 1e3 * t_pt,
+                    "obs_stream_GB": ys_pt.numel() * 8 / 1e9, "obs_stream_GBps": ys_pt.numel() * 8 / t_pt / 1e9,
+                    "frac_fp64_peak": F_STEP["Lorenz"] * B * T / t_pt / 1e12 / dfma_peak_tflops,
+                    "all_finite": bool(torch.isfinite(r_pt.nll).all()),
+                    "guard_fired_steps": None if r_pt.guard_fired is None else int(r_pt.guard_fired.sum()),
+                    "sample": "Lorenz, B=65536 x T=10000, y_t = own prediction-only trajectory + N(0, 1e-3), P0_sqrt = 1e-12 I"}
+                del ys_pt, r_pt
+            except Exception as exc:
+                extras["c2_per_trajectory_obs_error"] = f"{type(exc).__name__}: {exc}"
         # C1 (BASELINE config 1, the reference's own CPU-runnable case): ONE Lorenz trajectory,
         # T = 5,000 steps, prediction only, every step saved - a latency case, not a throughput case
         x1 = torch.ones(1, 3, dtype=torch.float64, device=dev)

@@ -22,43 +22,6 @@
 
 namespace odeu {
 
-ODEU_HD double copysign_hd(double mag, double sgn) {
-#ifdef __CUDA_ARCH__
-  return copysign(mag, sgn);
-#else
-  return std::copysign(mag, sgn);
-#endif
-}
-
-// 1/x and 1/sqrt(x) for NORMAL positive x without the slow-path branches of the CUDA library
-// versions (which cost ~12 and ~10 instructions plus a reconvergence scope each; nine of each per
-// Lorenz step): hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) + Newton to ~1 ulp.
-// x = 0 gives inf (rcp) / NaN (rsqrt after the correction): callers select around it.
-ODEU_HD double rcp_pos(double x) {
-#ifdef __CUDA_ARCH__
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
-#else
-  return 1.0 / x;
-#endif
-}
-ODEU_HD double rsqrt_pos(double x) {
-#ifdef __CUDA_ARCH__
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double t = x * y;
-  const double e = fma(-t, y, 1.0);            // 1 - x y^2
-  const double q = e * fma(0.375, e, 0.5);     // third-order correction
-  return fma(y, q, y);
-#else
-  return 1.0 / std::sqrt(x);
-#endif
-}
-
 // noise branch table of SURVEY section 3.2 (src/filters/sqrt_ekf.py:96-136,172-180)
 enum NoiseMode {
   NOISE_COVFN = 0,     // disable_cov_update=false, no Q:   P += covfn(eps)

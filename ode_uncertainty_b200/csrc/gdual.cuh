@@ -157,11 +157,21 @@ template <class S, int K> ODEU_HD GDual<S, K> d_cos(const GDual<S, K>& a) {
   return r;
 }
 ODEU_HD double d_sqrt(double a) { return sqrt(a); }
+// 1 / sqrt(a) for a normal positive a (no slow path, see rsqrt_pos); derivative -a' / (2 a sqrt(a))
+ODEU_HD double d_rsqrt(double a) { return rsqrt_pos(a); }
+
 ODEU_HD double d_log(double a) { return log(a); }
 ODEU_HD double d_abs(double a) { return fabs(a); }
 template <class S, int K> ODEU_HD GDual<S, K> d_sqrt(const GDual<S, K>& a) {
   GDual<S, K> r; r.v = d_sqrt(a.v);
   const S h = 0.5 / r.v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = h * a.d[k];
+  return r;
+}
+template <class S, int K> ODEU_HD GDual<S, K> d_rsqrt(const GDual<S, K>& a) {
+  GDual<S, K> r; r.v = d_rsqrt(a.v);
+  const S h = -0.5 * r.v * r.v * r.v;
 #pragma unroll
   for (int k = 0; k < K; ++k) r.d[k] = h * a.d[k];
   return r;

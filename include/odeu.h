@@ -49,12 +49,18 @@ typedef enum {
   ODEU_ODE_MULTI_HH = 6         /* src/ode/hodgkin_huxley.py:284-439 n = num_compartments * dim(variant) */
 } odeu_ode_id;
 
-/* src/solvers/__init__.py (explicit embedded RK only; DiffraxSolverBuilder is out of scope) */
+/* src/solvers/__init__.py */
 typedef enum {
   ODEU_SOLVER_RKF45 = 0,      /* src/solvers/rkf45.py     */
   ODEU_SOLVER_DOPRI65 = 1,    /* src/solvers/dopri65.py   */
   ODEU_SOLVER_BS32 = 2,       /* src/solvers/bs32.py      */
-  ODEU_SOLVER_HEUN_EULER = 3  /* src/solvers/heun_euler.py */
+  ODEU_SOLVER_HEUN_EULER = 3, /* src/solvers/heun_euler.py */
+  /* implicit plugins of DiffraxSolverBuilder(name=...) (src/solvers/diffrax_solver.py:16-140): one fixed
+   * step per call, Newton per stage, eps = 0.  diffrax is third-party and absent here: the published
+   * methods are restated (csrc/dirk.cuh), parity unpinned.  Served by the thread-per-trajectory kernels
+   * (odeu_ekf_run, odeu_ekf_grad_run, odeu_pf_run). */
+  ODEU_SOLVER_KVAERNO3 = 4,       /* DiffraxSolverBuilder(name="Kvaerno3")      ESDIRK 3(2), 4 stages */
+  ODEU_SOLVER_IMPLICIT_EULER = 5  /* DiffraxSolverBuilder(name="ImplicitEuler") the builder's default */
 } odeu_solver_id;
 
 /* src/covariance_update_functions/__init__.py */

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("ODEU_LIB", os.path.join(_HERE, "libodeu.so"))   # ODE
 
 # enums of include/odeu.h
 ODE_LORENZ, ODE_VAN_DER_POL, ODE_LOTKA_VOLTERRA, ODE_PENDULUM, ODE_LCAO, ODE_HODGKIN_HUXLEY, ODE_MULTI_HH = range(7)
-SOLVER_RKF45, SOLVER_DOPRI65, SOLVER_BS32, SOLVER_HEUN_EULER = range(4)
+SOLVER_RKF45, SOLVER_DOPRI65, SOLVER_BS32, SOLVER_HEUN_EULER, SOLVER_KVAERNO3, SOLVER_IMPLICIT_EULER = range(6)
 COV_DIAGONAL, COV_OUTER, COV_STATIC_DIAGONAL = range(3)
 GUARD_INTENDED, GUARD_REFERENCE, GUARD_INTENDED_FACTOR = range(3)
 

@@ -53,8 +53,7 @@ def instantiate(node: Any) -> Any:
             raise ValueError(f"class_path {node['class_path']!r}: no B200 plugin for module {mod!r}")
         klass = getattr(importlib.import_module(target), cls, None)
         if klass is None:
-            raise ValueError(f"class_path {node['class_path']!r}: {target} has no class {cls!r} "
-                             "(implicit diffrax solvers are outside the hot path, DESIGN.md section 8)")
+            raise ValueError(f"class_path {node['class_path']!r}: {target} has no class {cls!r}")
         kwargs = {k: instantiate(v) for k, v in (node.get("init_args") or {}).items()}
         return klass(**kwargs)
     if isinstance(node, dict):

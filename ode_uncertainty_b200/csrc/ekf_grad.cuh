@@ -15,6 +15,7 @@
 #pragma once
 #include "ekf_core.cuh"
 #include "gdual.cuh"
+#include "dirk.cuh"
 
 namespace odeu {
 
@@ -284,7 +285,9 @@ ODEU_HD void ekf_grad_trajectory(const GradArgs<Ode::NX, Ode::NP>& a, const long
   S nll = S(0.0);
   for (long long step = 0; step < a.T; ++step) {
     S xn[n], J[n][n];
-    if constexpr (KC == n) {
+    if constexpr (is_implicit<Tab>::value) {
+      dirk_step_generic<Ode, Tab, S>(t, h, x, th, xn, eps, J);
+    } else if constexpr (KC == n) {
       rk_step_generic<Ode, Tab, KC, S>(t, h, x, th, 0, true, xn, eps, J);
     } else {
 #pragma unroll 1

@@ -14,6 +14,7 @@
 #pragma once
 #include "ekf_core.cuh"
 #include "ekf_sqrt.cuh"
+#include "dirk.cuh"
 
 namespace odeu {
 
@@ -251,7 +252,23 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
     if (LK == -1 && a.skip_predict) {
       // single-step FilterCorrect: leave t, x, eps, P untouched
     } else {
-    if constexpr (SQ != 0) {
+    if constexpr (is_implicit<Tab>::value) {
+      // implicit solver plugin (dirk.cuh): the whole step Jacobian in one call; the factor form needs
+      // T = J P_sqrt
+      double Jd[n][n];
+      dirk_step_generic<Ode, Tab, double>(t, h, x, th, xn, eps, Jd);
+      if constexpr (SQ != 0) {
+        for (int i = 0; i < n; ++i)
+          for (int k = 0; k < n; ++k) {
+            double s_ = 0.0;
+            for (int j = 0; j < n; ++j) s_ = fma(Jd[i][j], P[j][k], s_);
+            J[i][k] = s_;
+          }
+      } else {
+        for (int i = 0; i < n; ++i)
+          for (int k = 0; k < n; ++k) J[i][k] = Jd[i][k];
+      }
+    } else if constexpr (SQ != 0) {
       // tangents seeded with the columns of P_sqrt like jmp_aux (src/utils.py:72-79): J holds T = J P_sqrt
       static_assert(SQ == 0 || KC == n, "factor form carries all tangent columns in one pass");
       rk_step_tangent<Ode, Tab, KC>(t, h, a.st, x, th, 0, true, xn, eps, J, P);

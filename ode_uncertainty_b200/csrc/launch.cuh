@@ -232,6 +232,14 @@ int launch_ekf(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream
   fill_scaled_tableau<Tab>(plan.desc.step_size, a.st);
   const int lk = select_lk<Ode>(io);
   int rc = 0;
+  if constexpr (is_implicit<Tab>::value) {      // implicit solver plugins: the generic variants only
+    if constexpr (n <= 4) {
+      if (io.guard_mode != ODEU_GUARD_INTENDED) rc = launch_ekf_variant<Ode, Tab, -1, 2>(a, io, stream);
+      else rc = launch_ekf_variant<Ode, Tab, -1>(a, io, stream);
+    } else {
+      rc = launch_ekf_variant<Ode, Tab, -1>(a, io, stream);
+    }
+  } else
   if constexpr (n <= 4) {
     if (io.guard_mode != ODEU_GUARD_INTENDED) {
       if (factor_fast_ok<Ode>(a, io, lk)) {
@@ -315,6 +323,8 @@ Launchers resolve_solver(int solver) {
     case ODEU_SOLVER_DOPRI65: return {&launch_ekf<Ode, TabDopri65>, &launch_pf<Ode, TabDopri65>, &launch_rhs<Ode>};
     case ODEU_SOLVER_BS32: return {&launch_ekf<Ode, TabBS32>, &launch_pf<Ode, TabBS32>, &launch_rhs<Ode>};
     case ODEU_SOLVER_HEUN_EULER: return {&launch_ekf<Ode, TabHeunEuler>, &launch_pf<Ode, TabHeunEuler>, &launch_rhs<Ode>};
+    case ODEU_SOLVER_KVAERNO3: return {&launch_ekf<Ode, TabKvaerno3>, &launch_pf<Ode, TabKvaerno3>, &launch_rhs<Ode>};
+    case ODEU_SOLVER_IMPLICIT_EULER: return {&launch_ekf<Ode, TabImplicitEuler>, &launch_pf<Ode, TabImplicitEuler>, &launch_rhs<Ode>};
     default: return {nullptr, nullptr, nullptr};
   }
 }

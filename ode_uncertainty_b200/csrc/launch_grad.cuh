@@ -129,7 +129,7 @@ void fill_rt_tableau(GradArgs<NXA, NPA>& a) {
 // Row-parallel kernel (ekf_rows.cuh) for ODE plugins that expose the row interface.
 template <class Ode, class Tab, class S>
 constexpr bool rows_static_ok() {
-  if constexpr (has_rows<Ode>::value) {
+  if constexpr (has_rows<Ode>::value && !is_implicit<Tab>::value) {
     return Ode::NX > 4 && RowsSmem<Ode, Tab, S, 32 / Ode::ROW_GROUPS>::bytes <= 227 * 1024;
   } else {
     return false;
@@ -235,6 +235,7 @@ int launch_grad(const odeu_plan& plan, const odeu_ekf_io* iop, const odeu_grad_i
   using Cfg = GradCfg<Ode>;
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, &g, a)) return rc;
+  if constexpr (!is_implicit<Tab>::value)       // (implicit solver plugins: thread-per-unit kernel below)
   if (rows_eligible<Ode, Tab, GDual<double, 1>>(io) || coop_eligible<Ode>(io)) {
     if (int rc = rows_eligible<Ode, Tab, GDual<double, 1>>(io) ? launch_rows<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)
                                         : launch_coop<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)) return rc;
@@ -285,6 +286,8 @@ GradLaunchFn resolve_grad_solver(int solver) {
     case ODEU_SOLVER_DOPRI65: return &launch_grad<Ode, TabDopri65>;
     case ODEU_SOLVER_BS32: return &launch_grad<Ode, TabBS32>;
     case ODEU_SOLVER_HEUN_EULER: return &launch_grad<Ode, TabHeunEuler>;
+    case ODEU_SOLVER_KVAERNO3: return &launch_grad<Ode, TabKvaerno3>;
+    case ODEU_SOLVER_IMPLICIT_EULER: return &launch_grad<Ode, TabImplicitEuler>;
     default: return nullptr;
   }
 }

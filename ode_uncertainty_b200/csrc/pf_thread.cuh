@@ -11,6 +11,7 @@
 // Box-Muller with single-precision transcendentals (see Philox::normal2).
 #pragma once
 #include "ekf_core.cuh"
+#include "dirk.cuh"
 
 namespace odeu {
 
@@ -121,7 +122,12 @@ ODEU_HD void pf_particle(const PfArgs<Ode::NX, Ode::NP>& a, const long long m) {
   bool have_spare = false;
   for (long long step = 0; step < a.T; ++step) {
     double xn[n];
-    rk_step_plain<Ode, Tab>(t, a.h, x, th, xn, eps);
+    if constexpr (is_implicit<Tab>::value) {
+      double Jd[n][n];      // (the step Jacobian comes with the Newton solve; unused here)
+      dirk_step_generic<Ode, Tab, double>(t, a.h, x, th, xn, eps, Jd);
+    } else {
+      rk_step_plain<Ode, Tab>(t, a.h, x, th, xn, eps);
+    }
     t = t + a.h;
     if (gid != 0 && !a.noise_free) {
       const unsigned long long gstep = (unsigned long long)(a.step_offset + step);

@@ -8,6 +8,7 @@
 // direction j (theta_j seeded 1, x0 carries d x0 / d theta_j), the outer dual seeds theta_k for the
 // PARTIAL derivative at fixed x0 (the closure `solver_jac_params_wrapper` captures x0 as a constant).
 #pragma once
+#include "dirk.cuh"
 #include "ekf_grad.cuh"
 
 namespace odeu {
@@ -29,6 +30,11 @@ struct SensArgs {
 // Plain RK step (propagating row b[1], rksolver.py:146-151) on an arbitrary scalar type.
 template <class Ode, class Tab, class D>
 ODEU_HD void rk_step_scalar(double t, double h, const D* x, const D* th, D* xn) {
+  if constexpr (is_implicit<Tab>::value) {       // implicit solver plugins (dirk.cuh)
+    D eps_[Ode::NX], J_[Ode::NX][Ode::NX];
+    dirk_step_generic<Ode, Tab, D>(t, h, x, th, xn, eps_, J_);
+    return;
+  } else {
   constexpr int n = Ode::NX;
   constexpr int St = Tab::S;
   D Ks[St][n];
@@ -48,6 +54,7 @@ ODEU_HD void rk_step_scalar(double t, double h, const D* x, const D* th, D* xn) 
     for (int j = 0; j < St; ++j)
       if (Tab::b(1, j) != 0.0) s = s + Ks[j][m] * Tab::b(1, j);
     xn[m] = x[m] + s * h;
+  }
   }
 }
 

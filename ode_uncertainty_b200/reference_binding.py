@@ -28,7 +28,7 @@ ODE_IDS = {"Lorenz": N.ODE_LORENZ, "VanDerPol": N.ODE_VAN_DER_POL, "LotkaVolterr
            "Pendulum": N.ODE_PENDULUM, "LCAO": N.ODE_LCAO, "HodgkinHuxley": N.ODE_HODGKIN_HUXLEY,
            "MultiCompartmentHodgkinHuxley": N.ODE_MULTI_HH}
 SOLVER_IDS = {"RKF45": N.SOLVER_RKF45, "Dopri65": N.SOLVER_DOPRI65, "BS32": N.SOLVER_BS32,
-              "HeunEuler": N.SOLVER_HEUN_EULER}
+              "HeunEuler": N.SOLVER_HEUN_EULER, "Kvaerno3": N.SOLVER_KVAERNO3, "ImplicitEuler": N.SOLVER_IMPLICIT_EULER}
 COV_IDS = {"DiagonalCovarianceUpdate": N.COV_DIAGONAL, "OuterCovarianceUpdate": N.COV_OUTER,
            "StaticDiagonalCovarianceUpdate": N.COV_STATIC_DIAGONAL}
 HH_VARIANT = {"full": 0, "reduced-1": 1, "reduced-4": 4}
@@ -53,10 +53,12 @@ def plan_kwargs(filter_builder, solver_builder, ode_builder, use_static_cov_fn: 
     """`odeu_plan_desc` for the reference's plugin objects (what jsonargparse instantiated from
     class_path / init_args, scripts/run_filter.py:31-47)."""
     oname, sname = type(ode_builder).__name__, type(solver_builder).__name__
+    if sname == "DiffraxSolverBuilder":       # the diffrax solver object's class names the method (diffrax_solver.py:29-34)
+        sname = getattr(solver_builder, "name", None) or type(solver_builder.solver).__name__
     if oname not in ODE_IDS:
         raise ValueError(f"Unsupported ODE builder: {oname}")
     if sname not in SOLVER_IDS:
-        raise ValueError(f"Unsupported solver builder for the B200 path: {sname} (explicit embedded RK only)")
+        raise ValueError(f"Unsupported solver builder for the B200 path: {sname}")
     variant, nc = 0, 0
     if oname in ("HodgkinHuxley", "MultiCompartmentHodgkinHuxley"):
         model = ode_builder.model if oname == "HodgkinHuxley" else ode_builder.single_compartment_model.model

@@ -175,3 +175,33 @@ class HeunEuler(RKSolverBuilder):
     @classmethod
     def build_c(cls):
         return _arr([0, 1.0])
+
+
+class DiffraxSolverBuilder(RKSolverBuilder):
+    """src/solvers/diffrax_solver.py:16-140: the implicit (stiff) solver plugin every shipped
+    Hodgkin-Huxley configuration selects (`name: Kvaerno3`, configs/params/hodgkinhuxley*.yaml:10-14).
+
+    The reference delegates to diffrax (`Kvaerno3` / `ImplicitEuler` with `Newton(rtol=atol=1e-8)`,
+    one fixed step per call, `eps = 0`); diffrax is third-party and not part of this image, so the
+    published methods are restated in CUDA (csrc/dirk.cuh: diagonally implicit RK, full Newton with a
+    dense LU per stage, step Jacobian and parameter tangents by the implicit function theorem).
+    Parity with diffrax is unpinned; the oracle is oracle/ref_torch.py::dirk_step."""
+    _IDS = {"Kvaerno3": N.SOLVER_KVAERNO3, "ImplicitEuler": N.SOLVER_IMPLICIT_EULER}
+
+    def __init__(self, name: str = "ImplicitEuler", step_size: float = 0.1) -> None:
+        SolverBuilder.__init__(self, step_size=step_size)
+        if name not in self._IDS:
+            raise ValueError(f"DiffraxSolverBuilder(name={name!r}): the B200 path serves {sorted(self._IDS)} "
+                             "(explicit methods: use the RKF45 / Dopri65 / BS32 / HeunEuler plugins)")
+        self.name = self.tableau = name
+        self.solver_id = self._IDS[name]
+        if name == "Kvaerno3":
+            g = 0.43586652150845899941601945
+            self.A = _arr([[0, 0, 0, 0], [g, g, 0, 0],
+                           [(-4 * g * g + 6 * g - 1) / (4 * g), (-2 * g + 1) / (4 * g), g, 0],
+                           [(6 * g - 1) / (12 * g), -1 / ((24 * g - 12) * g), (-6 * g * g + 6 * g - 1) / (6 * g - 3), g]])
+            self.c = _arr([0, 2 * g, 1, 1])
+        else:
+            self.A, self.c = _arr([[1.0]]), _arr([1.0])
+        self.b = np.stack([self.A[-1], self.A[-1]])         # stiffly accurate; no embedded error is used (eps = 0)
+        self.s = self.A.shape[0]

@@ -21,7 +21,7 @@ from ode_uncertainty_b200 import _native as N  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 SOLVERS = {"RKF45": N.SOLVER_RKF45, "Dopri65": N.SOLVER_DOPRI65, "BS32": N.SOLVER_BS32,
-           "HeunEuler": N.SOLVER_HEUN_EULER}
+           "HeunEuler": N.SOLVER_HEUN_EULER, "Kvaerno3": N.SOLVER_KVAERNO3, "ImplicitEuler": N.SOLVER_IMPLICIT_EULER}
 COVS = {"diagonal": N.COV_DIAGONAL, "outer": N.COV_OUTER, "static_diagonal": N.COV_STATIC_DIAGONAL}
 ODE_IDS = {
     "Lorenz": (N.ODE_LORENZ, 0, 0), "VanDerPol": (N.ODE_VAN_DER_POL, 0, 0),
@@ -96,6 +96,20 @@ CASES = {
 }
 
 
+# Implicit solver plugins (DiffraxSolverBuilder).  PARITY UNPINNED: diffrax is absent, the
+# oracle is this repository's own restatement (oracle/ref_torch.py::dirk_step).  Kept apart from CASES
+# (no reference-code fixture can exist); run against a live / cached Oracle-A by tests/test_implicit.py.
+IMPLICIT_CASES = {
+    # stiff regime of Van der Pol (damping 50): explicit RKF45 at h = 0.05 blows up, Kvaerno3 does not
+    "vdp_stiff_kvaerno3_obs": dict(ode="VanDerPol", solver="Kvaerno3", T=30, h=0.05, x0=[2., 0.], theta=[50.0],
+                                   obs=([0], 1), Rvar=1e-3, disable=True, Qw=[1., 1.], gamma=1e-4),
+    "lv_implicit_euler_predict": dict(ode="LotkaVolterra", solver="ImplicitEuler", T=25, h=0.05, x0=[1., 1.]),
+    # the shipped Hodgkin-Huxley shape (configs/params/hodgkinhuxley11_full.yaml): full model, Kvaerno3, h = 0.01
+    "hh_full_kvaerno3_temper": dict(ode="HodgkinHuxley/full", solver="Kvaerno3", T=25, t0=9.9, h=0.01,
+                                    x0=_hh_x0("full"), disable=True, Qw=[1.] * 8, gamma=1e-5, obs=([0], 1), Rvar=0.1),
+}
+
+
 def _lcao_x0(D, seed=7):
     """BASELINE config 5: positions ~ N(0, 1), velocities 0."""
     rng = np.random.default_rng(seed)
@@ -133,6 +147,11 @@ def ode_and_params(name):
 def materialize(spec):
     """Expand a spec into concrete arrays (deterministic; seeds fixed)."""
     ode, params, shape = ode_and_params(spec["ode"])
+    if "theta" in spec:        # non-default parameters, flat in builder order
+        flat, o, params = torch.tensor(spec["theta"], dtype=torch.float64), 0, dict(params)
+        for k, v in list(params.items()):
+            params[k] = flat[o:o + v.numel()].reshape(v.shape)
+            o += v.numel()
     n = shape[0] * shape[1]
     h = spec.get("h", 0.01)
     T = spec["T"]

@@ -113,7 +113,7 @@ int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
     }
     return emu_rows<Ode, Tab, double>(g, io.PT);
   }
-  if constexpr (coop_eligible_static<Ode>()) {
+  if constexpr (coop_eligible_static<Ode>() && !is_implicit<Tab>::value) {
     if (coop_eligible<Ode>(io)) {           // same routing as odeu_ekf_run
       GradArgs<Ode::NX, Ode::NP> g;
       if (int rc = fill_grad_args<Ode>(plan, io, nullptr, g)) return rc;
@@ -127,6 +127,14 @@ int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
   constexpr int KC = LaunchCfg<Ode>::KC;
   const int lk = select_lk<Ode>(io);
   auto run = [&](long long b, const Segment& sg) {
+    if constexpr (is_implicit<Tab>::value) {               // same routing as launch_ekf
+      if constexpr (n <= 4) {
+        if (io.guard_mode != ODEU_GUARD_INTENDED) ekf_trajectory<Ode, Tab, KC, -1, 2>(a, b, sg);
+        else ekf_trajectory<Ode, Tab, KC, -1>(a, b, sg);
+      } else {
+        ekf_trajectory<Ode, Tab, KC, -1>(a, b, sg);
+      }
+    } else
     if constexpr (n <= 4) {
       if (io.guard_mode != ODEU_GUARD_INTENDED) {          // same routing as launch_ekf
         if (factor_fast_ok<Ode>(a, io, lk)) {
@@ -195,6 +203,8 @@ int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p,
       case ODEU_SOLVER_DOPRI65: return emu_sens<Ode, TabDopri65>(plan, *s);
       case ODEU_SOLVER_BS32: return emu_sens<Ode, TabBS32>(plan, *s);
       case ODEU_SOLVER_HEUN_EULER: return emu_sens<Ode, TabHeunEuler>(plan, *s);
+      case ODEU_SOLVER_KVAERNO3: return emu_sens<Ode, TabKvaerno3>(plan, *s);
+      case ODEU_SOLVER_IMPLICIT_EULER: return emu_sens<Ode, TabImplicitEuler>(plan, *s);
     }
     return -2;
   }
@@ -204,6 +214,8 @@ int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p,
       case ODEU_SOLVER_DOPRI65: return emu_grad<Ode, TabDopri65>(plan, *e, *g);
       case ODEU_SOLVER_BS32: return emu_grad<Ode, TabBS32>(plan, *e, *g);
       case ODEU_SOLVER_HEUN_EULER: return emu_grad<Ode, TabHeunEuler>(plan, *e, *g);
+      case ODEU_SOLVER_KVAERNO3: return emu_grad<Ode, TabKvaerno3>(plan, *e, *g);
+      case ODEU_SOLVER_IMPLICIT_EULER: return emu_grad<Ode, TabImplicitEuler>(plan, *e, *g);
     }
     return -2;
   }
@@ -212,6 +224,8 @@ int emu_solver(const odeu_plan& plan, const odeu_ekf_io* e, const odeu_pf_io* p,
     case ODEU_SOLVER_DOPRI65: return e ? emu_ekf<Ode, TabDopri65>(plan, *e) : emu_pf<Ode, TabDopri65>(plan, *p);
     case ODEU_SOLVER_BS32: return e ? emu_ekf<Ode, TabBS32>(plan, *e) : emu_pf<Ode, TabBS32>(plan, *p);
     case ODEU_SOLVER_HEUN_EULER: return e ? emu_ekf<Ode, TabHeunEuler>(plan, *e) : emu_pf<Ode, TabHeunEuler>(plan, *p);
+    case ODEU_SOLVER_KVAERNO3: return e ? emu_ekf<Ode, TabKvaerno3>(plan, *e) : emu_pf<Ode, TabKvaerno3>(plan, *p);
+    case ODEU_SOLVER_IMPLICIT_EULER: return e ? emu_ekf<Ode, TabImplicitEuler>(plan, *e) : emu_pf<Ode, TabImplicitEuler>(plan, *p);
   }
   return -2;
 }
@@ -249,7 +263,7 @@ int emu_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, &g, a)) return rc;
   if (rows_eligible<Ode, Tab, GDual<double, 1>>(io)) return emu_rows<Ode, Tab, GDual<double, 1>>(a, nullptr);
-  if constexpr (coop_eligible_static<Ode>()) {
+  if constexpr (coop_eligible_static<Ode>() && !is_implicit<Tab>::value) {
     if (coop_eligible<Ode>(io)) return emu_coop<Ode, Tab, GDual<double, 1>>(a, nullptr);
   }
   using Cfg = GradCfg<Ode>;

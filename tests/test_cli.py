@@ -55,8 +55,11 @@ def test_config_tree_builds_the_b200_plugins(tmp_path):
 
 def test_unknown_plugins_fail_loudly(tmp_path):
     p = tmp_path / "bad.yaml"
-    p.write_text("solver_builder:\n  class_path: src.solvers.DiffraxSolverBuilder\n  init_args: {step_size: 0.01}\n")
-    with pytest.raises(ValueError, match="DiffraxSolverBuilder"):
+    p.write_text("solver_builder:\n  class_path: src.solvers.DiffraxSolverBuilder\n  init_args: {name: Tsit5, step_size: 0.01}\n")
+    with pytest.raises(ValueError, match="DiffraxSolverBuilder"):      # only Kvaerno3 / ImplicitEuler are served
+        cli.load_config(str(p))
+    p.write_text("solver_builder:\n  class_path: src.solvers.NoSuchSolver\n")
+    with pytest.raises(ValueError, match="NoSuchSolver"):
         cli.load_config(str(p))
     p.write_text("ode_builder:\n  class_path: somewhere.else.Thing\n")
     with pytest.raises(ValueError, match="no B200 plugin"):

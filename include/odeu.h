@@ -223,6 +223,21 @@ typedef struct {
 int odeu_ekf_grad_run(const odeu_plan* plan, const odeu_ekf_io* io, const odeu_grad_io* grad,
                       void* cuda_stream);
 
+/* Lock-step projected L-BFGS over R restarts on the device: the optimiser loop of
+ * scripts/run_parameter_estimation.py:599-667 (SciPy L-BFGS-B through jaxopt, one process per restart)
+ * without leaving the GPU; src/utils.py:15-36 is the reference's own projected L-BFGS.  Call pattern:
+ *   zt = starting points; evaluate (odeu_ekf_grad_run) -> odeu_lbfgs_step(first = 1)
+ *   repeat: evaluate the trial points zt -> odeu_lbfgs_step(first = 0)
+ * Every call advances every restart by one evaluation (Armijo backtracking on the projected path, m = 10
+ * curvature pairs, SciPy's stopping rules pgtol / ftol / maxiter).  workspace (zeroed before the first
+ * call) layout in doubles: z [R][p], g [R][p], d [R][p], f [R], alpha [R], S [R][10][p], Y [R][10][p],
+ * rho [R][10], then int32 meta [R][6] = {pairs, head, iterations, evaluations, status, ls trials};
+ * status: 0 running, 1 |proj grad| <= pgtol, 2 relative decrease <= ftol, 3 maxiter, 4 line search, 5 NaN. */
+int64_t odeu_lbfgs_workspace_doubles(int32_t R, int32_t p);
+int odeu_lbfgs_step(int32_t R, int32_t p, int32_t maxiter, int32_t first, double pgtol, double ftol,
+                    double* workspace_dev, double* zt_dev, const double* ft_dev, const double* gt_dev,
+                    const double* scale_dev, void* cuda_stream);
+
 /* Parameter-sensitivity weights of the process noise, replaces the `if parameter_sensitivity:` block
  * of nll() (scripts/run_parameter_estimation.py:750-769): one solver step from (t0, x0),
  *   w_i = sum_{k in idx} |d x1_i / d theta_k|,   w <- sqrt(n) w / |w|_2,   Q_sqrt = diag(w).

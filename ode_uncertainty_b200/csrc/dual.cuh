@@ -10,7 +10,12 @@
 
 namespace odeu {
 
+#ifdef ODEU_HOSTEMU
+// test-only host compilation of the kernel source (tests/host_emu.cu): no device code is generated
+#define ODEU_HD __host__ inline
+#else
 #define ODEU_HD __host__ __device__ __forceinline__
+#endif
 
 ODEU_HD double copysign_hd(double mag, double sgn) {
 #ifdef __CUDA_ARCH__

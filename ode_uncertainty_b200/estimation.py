@@ -87,9 +87,19 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
              gamma_noise_schedule: NoiseSchedule = ExponentialDecaySchedule(), lbfgs_maxiter: int = 200,
              num_random_runs: int = 0, seed: int = 7, initial_state_parametrized: bool = False,
              parameter_sensitivity: bool = False, device="cuda", verbose: bool = False,
-             _P0_sqrt: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+             _P0_sqrt: Optional[np.ndarray] = None, optimizer: str = "scipy", check_every: int = 16,
+             _z0: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """scripts/run_parameter_estimation.py:49-308 with the same keyword meaning (observations
-    are passed as arrays `ts_y`, `ys_x` instead of an H5 path)."""
+    are passed as arrays `ts_y`, `ys_x` instead of an H5 path).
+
+    optimizer: "scipy" - SciPy's L-BFGS-B per random run, like the reference (through jaxopt, :599), the
+    runs advancing in lock step (one host thread each; fine for tens of runs);  "device" - the
+    lock-step projected L-BFGS of csrc/lbfgs.cu: iterates, curvature history and line search of ALL
+    runs stay on the GPU, one `odeu_lbfgs_step` launch per batched objective evaluation, no host thread
+    per run and no device-to-host read inside a tempering stage (`check_every` = 0; a positive value
+    reads ONE flag every that many evaluations to stop early once every run has converged).  The device
+    optimiser is not SciPy's algorithm (projected path + Armijo instead of Cauchy point + More-Thuente),
+    so its iterates differ while the optima agree (tests/test_estimation.py)."""
     from scipy.optimize import minimize
 
     if measurement_matrix is None:
@@ -158,6 +168,18 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
             return nll.cpu().numpy(), g.cpu().numpy() * (hi - lo)        # d/d theta_norm
         return batch_fn
 
+    if optimizer not in ("scipy", "device"):
+        raise ValueError(f"optimizer must be 'scipy' or 'device', got {optimizer!r}")
+    if _z0 is not None:
+        z0 = np.asarray(_z0, dtype=np.float64).reshape(R, p)
+    if optimizer == "device":
+        if initial_state_parametrized:
+            raise ValueError("optimizer='device' does not serve initial_state_parametrized (x0(theta) is a host "
+                             "function of the ODE builder); use optimizer='scipy'")
+        return _optimize_device(plan, R, p, z0, lo, hi, default_sorted, opt_idx_sorted, perm, grad_idx_builder, x0_all,
+                                num_steps, dict(t0=t0, P0_sqrt=P0_sqrt, H=H, R_sqrt=R_sqrt, ys=ys_d, correct_flags=flags_d,
+                                                xy_index_map=ymap_d), Q_sqrt, parameter_sensitivity, gamma_noise_schedule,
+                                num_tempering_stages, final_gamma_zero, lbfgs_maxiter, check_every, opt_keys, sizes, verbose)
     params_optims = np.zeros((R, num_tempering_stages, p))
     nll_optims = np.zeros((R, num_tempering_stages))
     iters = np.zeros((R, num_tempering_stages), dtype=np.int64)
@@ -206,6 +228,80 @@ def optimize(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, mea
             "params_default": default_sorted[opt_idx_sorted], "params_name": np.array(names),
             "nll_optims": nll_optims, "num_lbfgs_iters": iters, "num_nll_evals": nfev,
             "num_nll_jac_evals": nfev.copy(), "gammas": np.array(gammas), "kernel_launches": launches}
+
+
+def _optimize_device(plan, R, p, z0, lo, hi, default_sorted, opt_idx_sorted, perm, grad_idx_builder, x0_all, num_steps,
+                     kw, Q_sqrt, parameter_sensitivity, schedule, num_stages, final_gamma_zero, maxiter, check_every,
+                     opt_keys, sizes, verbose) -> Dict[str, np.ndarray]:
+    """Tempered estimation with the device-resident lock-step L-BFGS (csrc/lbfgs.cu)."""
+    import ctypes as C
+
+    from . import _native as N
+    dev = x0_all.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    lib = N.lib()
+    lo_d, hi_d = torch.as_tensor(lo, **f64), torch.as_tensor(hi, **f64)
+    scale_d = (hi_d - lo_d).contiguous()
+    flat0 = torch.as_tensor(default_sorted, **f64).repeat(R, 1)
+    oi = torch.as_tensor(opt_idx_sorted, device=dev)
+    pm = torch.as_tensor(perm, device=dev)
+    zt = torch.as_tensor(z0, **f64).contiguous()
+    nws = int(lib.odeu_lbfgs_workspace_doubles(R, p))
+    ptr = lambda t_: C.c_void_p(t_.data_ptr())
+    evals = 0
+
+    def evaluate(gamma):
+        nonlocal evals
+        flat = flat0.clone()
+        flat[:, oi] = zt * scale_d + lo_d                                  # inv_normalize (:735-742), on the device
+        theta = flat[:, pm].contiguous()
+        qd = qd_tan = None
+        if parameter_sensitivity:
+            qd, qd_tan = param_sensitivity(plan, x0_all, grad_idx_builder, t0=kw["t0"], theta=theta)
+        nll, g = ekf_grad_run(plan, x0_all, num_steps, grad_idx_builder, theta=theta, Q_sqrt=Q_sqrt, gamma_sqrt=gamma ** 0.5,
+                              Q_sqrt_diag=qd, Q_sqrt_diag_tangent=qd_tan, **kw)
+        evals += 1
+        return nll, g.contiguous()
+
+    params_optims = np.zeros((R, num_stages, p))
+    nll_optims = np.zeros((R, num_stages))
+    iters = np.zeros((R, num_stages), dtype=np.int64)
+    nfev = np.zeros((R, num_stages), dtype=np.int64)
+    status = np.zeros((R, num_stages), dtype=np.int64)
+    gammas, host_reads = [], 0
+    max_evals = int(1.5 * maxiter) + 8
+    for stage in range(num_stages):
+        gamma = float(schedule.step(stage))
+        if final_gamma_zero and stage + 1 == num_stages:
+            gamma = 0.0
+        gammas.append(gamma)
+        ws = torch.zeros(nws, **f64)
+        meta = ws[nws - 3 * R:].view(torch.int32).view(R, 6)      # the workspace ends with the int32 bookkeeping
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        for k in range(max_evals):
+            nll, g = evaluate(gamma)
+            with torch.cuda.device(dev):
+                N.check(lib.odeu_lbfgs_step(R, p, int(maxiter), int(k == 0), 1e-5, 1e7 * np.finfo(float).eps, ptr(ws), ptr(zt),
+                                            ptr(nll), ptr(g), ptr(scale_d), st), "odeu_lbfgs_step")
+            if check_every > 0 and (k + 1) % check_every == 0:
+                host_reads += 1
+                if not bool((meta[:, 4] == 0).any()):                       # ONE flag: is any restart still running?
+                    break
+        z_fin = ws[: R * p].view(R, p)
+        f_fin = ws[3 * R * p: 3 * R * p + R]
+        zt = z_fin.clone().contiguous()                                     # warm start of the next stage (:626-651)
+        m_h = meta.cpu().numpy()                                            # the stage's results: one read
+        params_optims[:, stage] = z_fin.cpu().numpy() * (hi - lo) + lo
+        nll_optims[:, stage] = f_fin.cpu().numpy()
+        iters[:, stage], nfev[:, stage], status[:, stage] = m_h[:, 2], m_h[:, 3], m_h[:, 4]
+        if verbose:
+            print(f"stage {stage + 1}/{num_stages} gamma={gamma:g} best nll={nll_optims[:, stage].min():.6g}")
+    names = [k for k in opt_keys for _ in range(sizes[k])]
+    return {"params_inits": z0 * (hi - lo) + lo, "params_optims": params_optims,
+            "params_default": default_sorted[opt_idx_sorted], "params_name": np.array(names),
+            "nll_optims": nll_optims, "num_lbfgs_iters": iters, "num_nll_evals": nfev, "num_nll_jac_evals": nfev.copy(),
+            "gammas": np.array(gammas), "kernel_launches": evals, "lbfgs_status": status,
+            "host_reads_inside_stages": host_reads}
 
 
 def optimize_baseline(solver_builder, ode_builder, *, x0, ts_y, ys_x, measurement_matrix,

@@ -37,7 +37,7 @@ def hostemu():
         if stale:
             os.makedirs(os.path.dirname(HOSTEMU), exist_ok=True)
             subprocess.check_call(
-                ["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                ["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-DODEU_HOSTEMU",
                  "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-shared", src, "-o", HOSTEMU])
         _emu = C.CDLL(HOSTEMU)
         _emu.hostemu_ekf_run.argtypes = [C.POINTER(N.PlanDesc), C.POINTER(C.c_double), C.c_int,

@@ -9,13 +9,14 @@ the runner that mirrors the script's `main()`:
 
     python -m ode_uncertainty_b200.cli run_filter            --config cfg.yaml [--key value ...]
     python -m ode_uncertainty_b200.cli run_parameter_estimation optimize --config cfg.yaml
+    python -m ode_uncertainty_b200.cli run_parameter_estimation evaluate --config cfg.yaml
     python -m ode_uncertainty_b200.cli run_parameter_estimation_baseline optimize --config cfg.yaml
     python -m ode_uncertainty_b200.cli run_calibration       --config cfg.yaml
 
 Differences to the reference CLI: results are written as `.npz` with the reference's dataset names
 (h5py is not part of this image; an `.h5` output path is rewritten to `.npz`), and observation
 files (`y_path`) are `.npz` files with datasets `t`, `x` (what scripts/run_ode_solver.py stores).
-Keys the B200 path has no use for (`disable_pbar`, `num_processes`, `num_param_evals`) are ignored.
+Keys the B200 path has no use for (`disable_pbar`, `num_processes`) are ignored.
 """
 from __future__ import annotations
 
@@ -38,7 +39,7 @@ _MODULES = {
     "src.covariance_update_functions": "ode_uncertainty_b200.covariance_update_functions",
     "src.noise_schedules": "ode_uncertainty_b200.noise_schedules",
 }
-_IGNORED = {"disable_pbar", "num_processes", "num_param_evals"}
+_IGNORED = {"disable_pbar", "num_processes"}
 
 
 def instantiate(node: Any) -> Any:
@@ -106,10 +107,19 @@ def main(argv=None) -> Dict[str, np.ndarray]:
         return runners.run_filter(**cfg)
     if args.script == "run_calibration":
         return runners.calibration(**cfg)
-    if args.subcommand not in (None, "optimize"):
-        ap.error("only the `optimize` subcommand of run_parameter_estimation is served")
+    if args.subcommand not in (None, "optimize", "evaluate"):
+        ap.error("run_parameter_estimation serves the subcommands `optimize` and `evaluate`")
     output = cfg.pop("output", None)
     _load_observations(cfg)
+    if args.subcommand == "evaluate":                        # scripts/run_parameter_estimation.py:311-537
+        if args.script != "run_parameter_estimation":
+            ap.error("`evaluate` belongs to run_parameter_estimation")
+        res = estimation.evaluate(cfg.pop("filter_builder"), cfg.pop("solver_builder"), cfg.pop("ode_builder"), **cfg)
+        if output is not None:
+            os.makedirs(os.path.dirname(os.path.abspath(output)), exist_ok=True)
+            np.savez(output, **res)
+        return res
+    cfg.pop("num_param_evals", None)
     if args.script == "run_parameter_estimation_baseline":   # scripts/run_parameter_estimation_baseline.py:40-262
         res = estimation.optimize_baseline(cfg.pop("solver_builder"), cfg.pop("ode_builder"), **cfg)
         if output is not None:

@@ -304,6 +304,84 @@ def _optimize_device(plan, R, p, z0, lo, hi, default_sorted, opt_idx_sorted, per
             "host_reads_inside_stages": host_reads}
 
 
+def evaluate(filter_builder, solver_builder, ode_builder, *, x0, ts_y, ys_x, measurement_matrix,
+             params_range: Dict[str, Tuple[float, float]], gamma_noise_weights, num_param_evals: Dict[str, int],
+             params_optimized: Optional[Dict[str, bool]] = None, P0=None, t0: float = 0.0, tN: float = 80.0,
+             num_tempering_stages: int = 10, final_gamma_zero: bool = True, obs_noise_var: float = 0.1,
+             gamma_noise_schedule: NoiseSchedule = ExponentialDecaySchedule(), initial_state_parametrized: bool = False,
+             parameter_sensitivity: bool = False, device="cuda", **_unused) -> Dict[str, np.ndarray]:
+    """`evaluate()` of scripts/run_parameter_estimation.py:311-537: the NLL on the tensor grid
+    `linspace(min, max, num_param_evals[k])` over the optimised parameters (sorted-key order, :442-459),
+    for every tempering stage.  The reference evaluates the grid points one after the other and times
+    each call (`perf_counter_ns`, :496-522 - its only timing instrumentation); here the whole grid is the
+    batch axis of ONE launch per stage.  Returns the reference's datasets `param_evals`
+    [N_grid, p_opt], `nll_evals` [stages, N_grid], `gammas`, and `timings` (ns per grid point = launch
+    time / N_grid, first evaluation of the first stage dropped like :516-517)."""
+    import time
+
+    from .engine import ekf_run
+    if measurement_matrix is None:
+        raise ValueError("Measurement matrix is required!")              # :404-405
+    if gamma_noise_weights is None:
+        raise ValueError("Gamma noise weight vector is required!")       # :406-407
+    if params_range is None:
+        raise ValueError("Parameter ranges are required!")               # :408-409
+    if num_param_evals is None:
+        raise ValueError("Parameter evaluation counts are required!")    # :412-413
+    dev = torch.device(device)
+    plan = _plan_for(filter_builder, solver_builder, ode_builder)
+    n = plan.n
+    x0_raw = _arr(x0)
+    x0_built = ode_builder.build_initial_value(x0_raw, ode_builder.params).reshape(-1)
+    P0_sqrt = np.eye(n) * 1e-12 if P0 is None else np.linalg.cholesky(_arr(P0))
+    num_steps, flags, ymap = observation_schedule(t0, tN, solver_builder.h, ts_y)
+    H = _arr(measurement_matrix)
+    L = H.shape[0]
+    assert H.shape[1] == n, "Invalid measurement matrix!"
+    ys = np.einsum("ij,tj->ti", H, _arr(ys_x).reshape(-1, n))
+    w = _arr(gamma_noise_weights)
+    assert w.shape[0] == n, "Invalid gamma noise weight vector!"
+    keys_s, sizes, perm = param_layout(ode_builder)
+    opt = {k: True for k in keys_s} if params_optimized is None else params_optimized
+    default_sorted = np.concatenate([np.asarray(ode_builder.params[k], dtype=np.float64).reshape(-1) for k in keys_s])
+    axes = [np.linspace(params_range[k][0], params_range[k][1], int(num_param_evals[k])) for k in keys_s for _ in range(sizes[k])]
+    grid = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, len(axes))          # :455-457
+    off = np.cumsum([0] + [sizes[k] for k in keys_s])
+    opt_idx = np.concatenate([np.arange(off[i], off[i + 1]) for i, k in enumerate(keys_s) if opt[k]]).astype(np.int64)
+    flat = np.repeat(default_sorted[None, :], grid.shape[0], axis=0)
+    flat[:, opt_idx] = grid[:, opt_idx]                                  # non-optimised entries keep their defaults (:735-742)
+    theta = torch.as_tensor(flat[:, perm]).to(dev)
+    G = grid.shape[0]
+    if initial_state_parametrized:
+        xb, _ = initial_value_and_tangent(ode_builder, x0_raw, flat, opt_idx[:0])
+        x0_b = torch.as_tensor(xb).to(dev)
+    else:
+        x0_b = torch.as_tensor(np.repeat(x0_built[None, :], G, axis=0)).to(dev)
+    kw = dict(t0=t0, P0_sqrt=P0_sqrt, theta=theta, H=H, R_sqrt=np.eye(L) * obs_noise_var ** 0.5,
+              ys=torch.as_tensor(ys).to(dev), correct_flags=torch.as_tensor(flags.astype(np.uint8)).to(dev),
+              xy_index_map=torch.as_tensor(ymap).to(dev))
+    gidx = np.argsort(perm)[opt_idx]
+    nll_evals, gammas, timings = [], [], []
+    for stage in range(num_tempering_stages):
+        gamma = float(gamma_noise_schedule.step(stage))
+        if final_gamma_zero and stage + 1 == num_tempering_stages:
+            gamma = 0.0
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter_ns()
+        if parameter_sensitivity:                                          # Q_sqrt = diag(w(theta)) inside the loss (:750-769)
+            qd, _ = param_sensitivity(plan, x0_b, gidx, t0=t0, theta=theta, want_tangent=False)
+            nll, _ = ekf_grad_run(plan, x0_b, num_steps, gidx[:1], gamma_sqrt=gamma ** 0.5, Q_sqrt_diag=qd, **kw)
+        else:
+            nll = ekf_run(plan, x0_b, num_steps, Q_sqrt=np.diag(w), gamma_sqrt=gamma ** 0.5, want_final=False, minimal=True, **kw).nll
+        torch.cuda.synchronize(dev)
+        t2 = time.perf_counter_ns()
+        nll_evals.append(nll.cpu().numpy())
+        gammas.append(gamma)
+        timings += [(t2 - t1) / G] * (G - 1 if stage == 0 else G)
+    return {"param_evals": grid[:, opt_idx], "nll_evals": np.stack(nll_evals), "gammas": np.array(gammas),
+            "timings": np.array(timings)}
+
+
 def optimize_baseline(solver_builder, ode_builder, *, x0, ts_y, ys_x, measurement_matrix,
                       params_range: Dict[str, Tuple[float, float]],
                       params_optimized: Optional[Dict[str, bool]] = None, t0: float = 0.0, tN: float = 80.0,

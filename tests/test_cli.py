@@ -157,3 +157,72 @@ verbose: false
     saved = np.load(str(out)[:-3] + ".npz")
     assert set(["params_inits", "params_optims", "params_default", "params_name", "nll_optims", "num_lbfgs_iters",
                 "num_nll_evals", "num_nll_jac_evals"]).issubset(saved.files)
+
+
+@pytest.mark.gpu
+def test_evaluate_subcommand_grid_matches_single_evaluations(tmp_path):
+    """`run_parameter_estimation evaluate` (scripts/run_parameter_estimation.py:311-537): NLL on the
+    parameter grid for every tempering stage, the whole grid as ONE batch per stage; each grid value must
+    equal the single-parameter-set evaluation (Oracle-B) at that point."""
+    from oracle import ref_cpp as RC
+    from ode_uncertainty_b200 import Plan, _native as N, runners
+    truth, h, T = np.array([1.5, 1.0, 3.0, 1.0]), 0.01, 120
+    xs = runners.solve_trajectory(Plan(N.ODE_LOTKA_VOLTERRA, N.SOLVER_RKF45, h), [1.0, 1.0], T, theta_shared=truth)
+    ys = xs[1:] + np.random.default_rng(2).normal(0, 0.05, (T, 2))
+    yp = tmp_path / "obs.npz"
+    np.savez(yp, t=h * np.arange(1, T + 1), x=ys)
+    p = tmp_path / "eval.yaml"
+    p.write_text(f"""
+output: {tmp_path / "eval.h5"}
+filter_builder:
+  class_path: src.filters.SQRT_EKF
+  init_args:
+    disable_cov_update: true
+solver_builder:
+  class_path: src.solvers.RKF45
+  init_args:
+    step_size: {h}
+ode_builder:
+  class_path: src.ode.LotkaVolterra
+x0: '[[1.0, 1.0]]'
+t0: 0.0
+tN: {T * h}
+y_path: {yp}
+measurement_matrix: '[[1, 0], [0, 1]]'
+params_range:
+  alpha: [0.5, 3.0]
+  beta: [0.3, 2.0]
+  gamma: [1.0, 5.0]
+  delta: [0.3, 2.0]
+params_optimized:
+  alpha: true
+  beta: false
+  gamma: true
+  delta: false
+num_param_evals:
+  alpha: 5
+  beta: 1
+  gamma: 4
+  delta: 1
+num_tempering_stages: 2
+final_gamma_zero: true
+obs_noise_var: 0.0025
+gamma_noise_schedule:
+  class_path: src.noise_schedules.LinearDecaySchedule
+  init_args:
+    init_noise_log: -2.0
+    decay_rate: 2
+gamma_noise_weights: '[1, 1]'
+""")
+    res = cli.main(["run_parameter_estimation", "evaluate", "--config", str(p)])
+    assert res["param_evals"].shape == (20, 2) and res["nll_evals"].shape == (2, 20)
+    assert res["gammas"].tolist() == [1e-2, 0.0] and res["timings"].shape == (39,)
+    np.testing.assert_allclose(np.unique(res["param_evals"][:, 0]), np.linspace(0.5, 3.0, 5))     # alpha (sorted keys: alpha, gamma)
+    np.testing.assert_allclose(np.unique(res["param_evals"][:, 1]), np.linspace(1.0, 5.0, 4))
+    for gi in (0, 7, 19):
+        th = np.array([res["param_evals"][gi, 0], 1.0, res["param_evals"][gi, 1], 1.0])           # builder order alpha, beta, gamma, delta
+        for si, g in enumerate(res["gammas"]):
+            o = RC.ekf_run("LotkaVolterra", "RKF45", h, [[1.0, 1.0]], T, theta=th, Q_sqrt=np.eye(2), gamma_sqrt=g ** 0.5,
+                           H=np.eye(2), R_sqrt=np.eye(2) * 0.05, ys=ys, correct_flags=np.ones(T, np.uint8),
+                           xy_index_map=np.arange(T), disable=True, guard="intended")
+            assert abs(res["nll_evals"][si, gi] - o["nll"][0]) <= 1e-8 * abs(o["nll"][0])

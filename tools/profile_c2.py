@@ -1,6 +1,6 @@
 """One launch of each C2 kernel (Lorenz / Van der Pol, predict + correct) for ncu captures.
 
-    python tools/profile_c2.py [T] [system]
+    python tools/profile_c2.py [T] [system ...] [--guard=reference|intended]
 """
 import os
 import sys
@@ -14,7 +14,12 @@ import bench  # noqa: E402
 from ode_uncertainty_b200 import Plan, _native as N, ekf_run  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-systems = sys.argv[2:] or ["Lorenz", "VanDerPol"]
+guard = "reference"
+args = [a for a in sys.argv[2:] if not a.startswith("--")]
+for a in sys.argv[2:]:
+    if a.startswith("--guard="):
+        guard = a.split("=", 1)[1]
+systems = args or ["Lorenz", "VanDerPol"]
 dev = torch.device("cuda:0")
 B = 65536
 for system in systems:
@@ -27,6 +32,6 @@ for system in systems:
     ymap = torch.arange(T, dtype=torch.int64, device=dev)
     for _ in range(2):
         r = ekf_run(plan, x0, T, t0=w["t0"], P0_sqrt=w["P0_sqrt"], H=w["H"], R_sqrt=w["R_sqrt"],
-                    ys=ys, correct_flags=flags, xy_index_map=ymap)
+                    ys=ys, correct_flags=flags, xy_index_map=ymap, guard=guard)
     torch.cuda.synchronize()
     print(system, "nll mean", float(r.nll.mean()), "finite", bool(torch.isfinite(r.nll).all()))

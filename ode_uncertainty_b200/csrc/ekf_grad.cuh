@@ -42,6 +42,12 @@ struct GradArgs {
   double* nll;                   // [B]
   double* grad;                  // [p_opt][B]
   double* xT;                    // [n][B] nullable (value part of the final mean)
+  // full output contract of unroll() for the row kernel's NLL-only instantiation (scripts/run_filter.py:
+  // 219-222): strided trajectory slots, last error estimate / pre-update y_hat, S / time, resume covariance
+  long long save_interval;       // 0: none
+  const double* P0b;             // [n*n][B] per-trajectory initial covariance, or null (= P0s)
+  double* epsT; double* yhatT; double* ST; double* tT;
+  double* out_t; double* out_x; double* out_eps; double* out_P; double* out_yhat; double* out_S;
   double P0s[NX * NX], GQ[NX * NX], H[NX * NX], R[NX * NX];
   double theta_shared[NP];
   // run-time copy of the tableau for the rolled stage loops of the cooperative kernel

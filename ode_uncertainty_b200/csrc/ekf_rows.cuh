@@ -148,6 +148,9 @@ struct RowThread {
   S Kreg[n];       // register-resident stage tangent column
   S W[n];          // scratch: Y / row of P
   S ph[LM], Krow[LM], dvec[LM];
+  // trajectory-output bookkeeping (NLL-only instantiation, see save_step)
+  long long next_save, slot;
+  bool obs_fresh;
 
   // ---- shared memory addressing
   ODEU_HD static constexpr int pe(int e) { return (e / PR) * (TB * PR) + (e % PR); }
@@ -203,7 +206,15 @@ struct RowThread {
       THp(sm)[k * TB] = v;
     }
     seed_x0(a);
-    for (int k = 0; k < NP2; ++k) Prow(sm, r)[pe(k)] = S(k < n ? a.P0s[r * n + k] : 0.0);
+    for (int k = 0; k < NP2; ++k) {
+      S v = S(k < n ? a.P0s[r * n + k] : 0.0);
+      if (a.P0b && k < n) {
+#pragma unroll
+        for (int u = 0; u < NL; ++u) lane_set(v, u, a.P0b[((long long)r * n + k) * a.B + b[u]]);
+      }
+      Prow(sm, r)[pe(k)] = v;
+    }
+    next_save = a.save_interval; slot = 1; obs_fresh = false;
     for (int j = 0; j < ST; ++j) kp[j] = S(0.0);
     for (int m = 0; m < n; ++m) Kreg[m] = S(0.0);
   }
@@ -515,6 +526,7 @@ struct RowThread {
         }
       }
     }
+    publish_obs(a, xs, Sm, L);
     Mask2 all_tiny = mask_true();
 #pragma unroll
     for (int j = 0; j < LM; ++j) {
@@ -585,6 +597,76 @@ struct RowThread {
       }
     }
   }
+  // The PRE-update y_hat = y - d and S that the reference keeps in its state (sqrt_ekf.py:370-372): thread
+  // r = 0 of the trajectory writes them into the upcoming trajectory slot and the final-state arrays.
+  ODEU_HD void publish_obs(const Args& a, const S* xs, const S (*Sm)[LM], int L) {
+    if constexpr (!is_gdual<S>::value && NL == 1) {
+      obs_fresh = true;
+      if (r != 0 || !active[0]) return;
+      if (!(a.save_interval > 0 || a.yhatT || a.ST)) return;
+      const bool to_slot = a.save_interval > 0 && next_save <= a.T;
+      for (int l = 0; l < L; ++l) {
+        double yh;
+        if (a.h_sel_all) yh = lane_get(xs[a.h_sel[l] * TB], 0);
+        else {
+          yh = lane_get(xs[0], 0) * a.H[l * n];
+          for (int j = 1; j < n; ++j) yh = yh + lane_get(xs[j * TB], 0) * a.H[l * n + j];
+        }
+        if (to_slot && a.out_yhat) a.out_yhat[(slot * L + l) * a.B + b[0]] = yh;
+        if (a.yhatT) a.yhatT[l * a.B + b[0]] = yh;
+        for (int m = 0; m < L; ++m) {
+          const double sv = lane_get(Sm[l][m], 0);
+          if (to_slot && a.out_S) a.out_S[(slot * L * L + l * L + m) * a.B + b[0]] = sv;
+          if (a.ST) a.ST[(l * L + m) * a.B + b[0]] = sv;
+        }
+      }
+    }
+  }
+  // slot 0 (initial state) and, after a step, the strided save of run_filter.py:219-222: thread (trajectory,
+  // row r) writes x_r, eps_r and row r of P (still in W after phase_mp / phase_update)
+  ODEU_HD void save_initial(const Args& a, S* sm) {
+    if constexpr (!is_gdual<S>::value && NL == 1) {
+      if (a.save_interval <= 0 || !active[0]) return;
+      const long long B = a.B, bb = b[0];
+      if (a.out_x) a.out_x[(long long)r * B + bb] = lane_get(x, 0);
+      if (a.out_eps) a.out_eps[(long long)r * B + bb] = 0.0;
+      if (a.out_P)
+        for (int k = 0; k < n; ++k) a.out_P[((long long)r * n + k) * B + bb] = lane_get(Prow(sm, r)[pe(k)], 0);
+      if (r == 0) {
+        const int L = a.L;
+        for (int l = 0; l < L; ++l) if (a.out_yhat) a.out_yhat[l * B + bb] = 0.0;
+        for (int l = 0; l < L * L; ++l) if (a.out_S) a.out_S[l * B + bb] = 0.0;
+        if (bb == 0 && a.out_t) a.out_t[0] = t;
+      }
+    }
+  }
+  ODEU_HD void save_step(const Args& a, long long step) {
+    if constexpr (!is_gdual<S>::value && NL == 1) {
+      if (a.save_interval <= 0 || step + 1 != next_save) return;
+      if (active[0]) {
+        const long long B = a.B, bb = b[0];
+        if (a.out_x) a.out_x[(slot * n + r) * B + bb] = lane_get(x, 0);
+        if (a.out_eps) a.out_eps[(slot * n + r) * B + bb] = lane_get(epsr, 0);
+        if (a.out_P) {
+#pragma unroll
+          for (int k = 0; k < n; ++k) a.out_P[(slot * n * n + (long long)r * n + k) * B + bb] = lane_get(W[k], 0);
+        }
+        if (r == 0) {
+          const int L = a.L;
+          if (!obs_fresh) {      // no update since the previous slot: the state still holds the older values
+            for (int l = 0; l < L; ++l)
+              if (a.out_yhat) a.out_yhat[(slot * L + l) * B + bb] = a.out_yhat[((slot - 1) * L + l) * B + bb];
+            for (int l = 0; l < L * L; ++l)
+              if (a.out_S) a.out_S[(slot * L * L + l) * B + bb] = a.out_S[((slot - 1) * L * L + l) * B + bb];
+          }
+          if (bb == 0 && a.out_t) a.out_t[slot] = t;
+        }
+      }
+      obs_fresh = false;
+      ++slot;
+      next_save += a.save_interval;
+    }
+  }
   // x_r += K_r d;  P+[r, :] = P[r, :] - K_r (H P)[:, :] - G_r K^T
   ODEU_HD void phase_update(const Args& a, S* sm) {
     const int L = obs_dim(a);
@@ -610,6 +692,8 @@ struct RowThread {
       if (chunk == 0) {
         if (r == 0 && a.nll) a.nll[b[u]] = lane_get(nll, u);
         if (a.xT) a.xT[r * a.B + b[u]] = lane_get(x, u);
+        if (a.epsT) a.epsT[r * a.B + b[u]] = lane_get(epsr, u);
+        if (a.tT && r == 0 && b[u] == 0) a.tT[0] = t;
         if (PT)
           for (int k = 0; k < n; ++k) PT[((long long)r * n + k) * a.B + b[u]] = lane_get(Prow(sm, r)[pe(k)], u);
       }
@@ -633,6 +717,7 @@ ekf_rows_kernel(const __grid_constant__ GradArgs<Ode::NX, Ode::NP> a, double* PT
   constexpr int NL = lanes_of<S>::value;
   th.init(a, (long long)blockIdx.x * (TB * NL) + lane % TB, lane % TB, lane / TB, threadIdx.x >> 5, sm);
   __syncthreads();
+  th.save_initial(a, sm);
   for (long long step = 0; step < a.T; ++step) {
 #pragma unroll 1
     for (int i = 0; i < Tab::S; ++i) {
@@ -667,6 +752,7 @@ ekf_rows_kernel(const __grid_constant__ GradArgs<Ode::NX, Ode::NP> a, double* PT
       th.phase_update(a, sm);
     }
     th.phase_store(sm);
+    th.save_step(a, step);
   }
   __syncthreads();
   th.finish(a, PT, sm);

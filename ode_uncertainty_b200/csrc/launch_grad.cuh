@@ -24,8 +24,8 @@ int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad
   constexpr int NP = Ode::NP;
   if (io.B <= 0 || io.T < 0) { set_error("odeu_ekf_grad_run: B must be > 0 and T >= 0"); return -1; }
   if (io.L < 0 || io.L > n) { set_error("odeu_ekf_grad_run: L=%d outside [0, n=%d]", io.L, n); return -1; }
-  if (!io.x0 || !io.P0_sqrt) { set_error("odeu_ekf_grad_run: x0 and a shared P0_sqrt are required"); return -1; }
-  if (io.P0) { set_error("odeu_ekf_grad_run: per-trajectory P0 is not supported"); return -1; }
+  if (!io.x0 || (!io.P0_sqrt && !io.P0)) { set_error("odeu_ekf_grad_run: x0 and P0_sqrt (or P0) are required"); return -1; }
+  if (io.P0 && gp) { set_error("odeu_ekf_grad_run: per-trajectory P0 is not supported"); return -1; }
   if (gp && (io.cov_scale_batch || io.nll_nan_to_num)) { set_error("odeu_ekf_grad_run: the calibration-sweep options are served by odeu_ekf_run"); return -1; }
   if (gp && (g.p_opt < 1 || g.p_opt > ODEU_MAX_GRAD || !g.idx || !g.grad)) {
     set_error("odeu_ekf_grad_run: need 1..%d parameter indices and a grad buffer", ODEU_MAX_GRAD);
@@ -48,7 +48,14 @@ int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad
   a.qdiag = io.Q_sqrt_diag_batch; a.qdiag_tan = gp ? g.Q_sqrt_diag_tangent : nullptr; a.q_gamma = io.gamma_sqrt;
   a.flags = io.correct_flags; a.ymap = (const long long*)io.xy_index_map;
   a.nll = io.nll; a.grad = g.grad; a.xT = io.xT;
+  // (only the NLL-only row kernel honours the trajectory / final-state outputs below; the eligibility
+  // tests keep every other kernel away from runs that ask for them)
+  a.save_interval = gp ? 0 : io.save_interval; a.P0b = gp ? nullptr : io.P0;
+  a.epsT = io.epsT; a.yhatT = io.yhatT; a.ST = io.ST; a.tT = io.tT;
+  a.out_t = io.out_t; a.out_x = io.out_x; a.out_eps = io.out_eps; a.out_P = io.out_P;
+  a.out_yhat = io.out_yhat; a.out_S = io.out_S;
   for (int i = 0; i < n * n; ++i) { a.P0s[i] = 0.0; a.GQ[i] = 0.0; a.H[i] = 0.0; a.R[i] = 0.0; }
+  if (io.P0_sqrt)
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) {
       double s = 0.0;
@@ -139,8 +146,12 @@ template <class Ode, class Tab, class S>
 bool rows_eligible(const odeu_ekf_io& io) {
   if constexpr (rows_static_ok<Ode, Tab, S>()) {
     static const bool off = getenv("ODEU_NO_ROWS") != nullptr;   // A/B switch for measurements
-    return !off && io.L <= ROWS_LMAX && !io.cov_scale_batch && !io.nll_nan_to_num && !io.P0 && io.save_interval == 0 && !io.skip_predict && !io.epsT &&
-           !io.yhatT && !io.ST && !io.tT;
+    // the NLL-only instantiation (S = double) serves the full output contract of unroll(): strided slots,
+    // eps / y_hat / S / t, per-trajectory P0 (resume); the gradient instantiation does not need it
+    constexpr bool full = std::is_same<S, double>::value;
+    return !off && io.L <= ROWS_LMAX && !io.cov_scale_batch && !io.nll_nan_to_num && !io.skip_predict &&
+           io.guard_mode == ODEU_GUARD_INTENDED &&
+           (full || (!io.P0 && io.save_interval == 0 && !io.epsT && !io.yhatT && !io.ST && !io.tT));
   } else {
     return false;
   }
@@ -173,7 +184,7 @@ int launch_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) 
     if constexpr (std::is_same<S, double>::value && std::is_same<Tab, TabRKF45>::value &&
                   rows_static_ok<Ode, Tab, V2d>()) {
       static const bool two_wide = getenv("ODEU_ROWS_2WIDE") != nullptr;
-      if (two_wide) {
+      if (two_wide && a.save_interval == 0 && !a.P0b && !a.epsT && !a.yhatT && !a.ST && !a.tT) {
         if (a.L == Ode::ROW_GROUPS && a.has_obs) return launch_rows_lt<Ode, Tab, V2d, Ode::ROW_GROUPS>(a, PT, stream);
         return launch_rows_lt<Ode, Tab, V2d, 0>(a, PT, stream);
       }

@@ -70,6 +70,7 @@ int emu_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
         const int tl = k % TB, g = (k / TB) % Ode::ROW_GROUPS, q = k / (TB * Ode::ROW_GROUPS);
         th[k].init(a, cta * UPC + tl, tl, g, q, sm.data());
       }
+      for (auto& t : th) t.save_initial(a, sm.data());
       for (long long step = 0; step < a.T; ++step) {
         for (int i = 0; i < a.rt_S; ++i) {
           for (auto& t : th) t.stage_a_rt(a, i, sm.data());
@@ -94,6 +95,7 @@ int emu_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
           for (auto& t : th) t.phase_update(a, sm.data());
         }
         for (auto& t : th) t.phase_store(sm.data());
+        for (auto& t : th) t.save_step(a, step);
       }
       for (auto& t : th) t.finish(a, PT, sm.data());
     }

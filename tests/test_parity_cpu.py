@@ -209,3 +209,34 @@ np.save(sys.argv[1], np.concatenate([c["nll"].ravel(), c["xT"].ravel(), c["PT"].
             subprocess.check_call([sys.executable, "-c", code, out], cwd=root, env=e)
             outs.append(np.load(out))
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("backend", ["hostemu", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("name", ["hh_r1_rkf45_temper", "c3_mhh_r1_rkf45_temper"])
+def test_row_kernel_serves_the_full_output_contract(name, backend):
+    """run_filter on the Hodgkin-Huxley family (strided trajectory slots, eps, pre-update
+    y_hat / S, t, resume from a per-trajectory P0) is served by the row-parallel kernel, not by the slow
+    one-column-per-pass thread kernel: every output against the Oracle-A fixture, strided saves equal the
+    dense ones, and a run cut in two (second leg resumed from xT / PT / tT) equals the uncut run bitwise."""
+    import util as U
+    spec = cases.CASES[name]
+    gold = cases.load_golden(name)
+    batch = 19 if backend == "gpu" else 2
+    dense = cases.run_product(backend, spec, save_interval=1, batch=batch)
+    cases.compare(dense, gold, spec, b=batch - 1)
+    strided = cases.run_product(backend, spec, save_interval=7, batch=batch)
+    for k in ("t", "x", "eps", "P", "y_hat", "S"):
+        np.testing.assert_array_equal(strided["traj"][k], dense["traj"][k][::7], err_msg=k)
+    m = cases.materialize(spec)
+    plan = cases.make_plan_for(spec)
+    x0 = np.repeat(m["x0"].reshape(1, -1).numpy(), batch, axis=0)
+    kw = dict(Q_sqrt=m["Q"].numpy(), gamma_sqrt=m["gamma"] ** 0.5, H=m["H"].numpy(), R_sqrt=m["Rs"].numpy(), ys=m["ys"].numpy())
+    T, T1 = m["T"], 17
+    a = U.run_ekf(backend, plan, x0, T1, t0=m["t0"], P0_sqrt=m["P0s"].numpy(), correct_flags=m["flags"], xy_index_map=m["ymap"], **kw)
+    b = U.run_ekf(backend, plan, a["xT"], T - T1, t0=a["tT"], P0=a["PT"], correct_flags=m["flags"][T1:], xy_index_map=m["ymap"][T1:], **kw)
+    np.testing.assert_array_equal(b["xT"], dense["xT"])
+    np.testing.assert_array_equal(b["PT"], dense["PT"])
+    assert b["tT"] == dense["tT"]
+    np.testing.assert_array_equal(b["yhatT"], dense["traj"]["y_hat"][-1])
+    np.testing.assert_array_equal(b["ST"], dense["traj"]["S"][-1])
+    np.testing.assert_array_equal(b["epsT"], dense["traj"]["eps"][-1])

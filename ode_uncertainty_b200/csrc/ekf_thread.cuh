@@ -126,6 +126,43 @@ ODEU_HD double ws_load(const double* p) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-async staging of the PER-TRAJECTORY observation stream (north_star: "observations ... streamed
+// in with ... TMA-staged loads").  The stream is ys [T_obs][L][B]: for one warp (32 consecutive
+// trajectories) and one observation row it is a contiguous 256-byte line.  A warp stages OBS_CH steps
+// at a time into its own shared-memory ring (2 buffers x OBS_CH x L lines) with `cp.async.bulk`
+// (SASS UBLKCP) completing on an mbarrier (SYNCS): lane i of the warp looks up flag / index map of
+// step i of the chunk and issues the L line copies of that step, one lane arms the barrier with the
+// byte count, and the chunk after the current one is always in flight while the current one is
+// consumed.  Device only; needs B % 32 == 0 (whole, 256-byte aligned lines).
+constexpr int OBS_CH = 8;
+struct ObsStage {
+  double* buf;                  // [2][OBS_CH][L][32]
+  unsigned long long* bar;      // [2] mbarriers
+  unsigned* parity;             // bit k: phase parity to wait for on barrier k (persists across work items)
+};
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#endif
+
 struct Segment {
   long long step0, step1;   // steps of this segment
   bool first, last;         // first: state comes from x0/P0/t0; last: final outputs are written
@@ -133,6 +170,7 @@ struct Segment {
                             // block of 32 trajectories
   const long long* last_obs;  // nullable: last step with an observation, found once per launch
                             // (find_last_obs_kernel); null = this trajectory scans the flags itself
+  const ObsStage* stg;      // nullable: shared-memory staging of per-trajectory observations (device only)
 };
 
 // jnp.nan_to_num of one log-likelihood term (calibration sweep, :218 of the calibration script)
@@ -147,7 +185,32 @@ ODEU_HD double nll_term(double v, int nan_to_num) {
 // SQ selects the covariance representation: 0 = full P (intended guard), 1 = factor form with the
 // structured QRs (H = [I_LK 0], lower-triangular R_sqrt, diagonal process-noise block), 2 = factor
 // form, generic.  In the factor forms `P` below holds P_sqrt.
-template <class Ode, class Tab, int KC, int LK, int SQ = 0>
+#ifdef __CUDA_ARCH__
+// issue the line copies of the OBS_CH steps starting at `s_begin` into ring buffer `k` (whole warp)
+template <int LK, int NXA, int NPA>
+__device__ __forceinline__ void stage_issue(const EkfArgs<NXA, NPA>& a, const Segment& sg, long long s_begin, int k, long long b0) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();                                          // every lane is done reading this buffer
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  bool fl = false;
+  long long oi = 0;
+  const long long s = s_begin + lane;
+  if (lane < OBS_CH && s < sg.step1) {
+    fl = a.flags[s] != 0;
+    if (fl) oi = a.ymap[s];
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, fl);
+  if (lane == 0) mbar_expect_tx(sg.stg->bar + k, (unsigned)__popc(m) * LK * 256u);
+  __syncwarp();
+  if (fl) {
+#pragma unroll
+    for (int l = 0; l < LK; ++l)
+      bulk_g2s(sg.stg->buf + ((k * OBS_CH + lane) * LK + l) * 32, a.ys + (oi * LK + l) * a.B + b0, 256u, sg.stg->bar + k);
+  }
+}
+#endif
+
+template <class Ode, class Tab, int KC, int LK, int SQ = 0, bool STG = false>
 ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long b, const Segment& sg) {
   constexpr int n = Ode::NX;
   const double cov_scale = a.scale_b ? a.scale_b[b] : a.cov_scale;
@@ -247,6 +310,21 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
   }
 
   for (long long step = sg.step0; step < sg.step1; ++step) {
+#ifdef __CUDA_ARCH__
+    if constexpr (STG && LK > 0) {       // chunk boundary: next chunk into flight, then wait for this one
+      const long long rel = step - sg.step0;
+      if ((rel & (OBS_CH - 1)) == 0) {
+        const int k = (int)(rel / OBS_CH) & 1;
+        const long long b0 = b - (threadIdx.x & 31);
+        if (rel == 0) stage_issue<LK>(a, sg, step, 0, b0);
+        if (step + OBS_CH < sg.step1) stage_issue<LK>(a, sg, step + OBS_CH, k ^ 1, b0);
+        mbar_wait(sg.stg->bar + k, (*sg.stg->parity >> k) & 1u);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) *sg.stg->parity ^= (1u << k);
+        __syncwarp();
+      }
+    }
+#endif
     // ---- predict (src/filters/sqrt_ekf.py:92-197)
     double xn[n], J[n][n];
     if (LK == -1 && a.skip_predict) {
@@ -334,8 +412,18 @@ ODEU_HD void ekf_trajectory(const EkfArgs<Ode::NX, Ode::NP>& a, const long long 
         const double* yp = a.ys_per_traj ? a.ys + oi * LK * B + b : a.ys + oi * LK;   // one address, one stride
         const long long ystr = a.ys_per_traj ? B : 1;
         double y[LK];
+#ifdef __CUDA_ARCH__
+        if constexpr (STG) {
+          const long long rel = step - sg.step0;
+          const double* ysm = sg.stg->buf + ((((int)(rel / OBS_CH) & 1) * OBS_CH + (int)(rel & (OBS_CH - 1))) * LK) * 32 + (threadIdx.x & 31);
+#pragma unroll
+          for (int l = 0; l < LK; ++l) y[l] = ysm[l * 32];
+        } else
+#endif
+        {
 #pragma unroll
         for (int l = 0; l < LK; ++l) y[l] = yp[l * ystr];
+        }
         if constexpr (SQ == 1)
           nll += nll_term(correct_factor_lead<n, LK>(a.R, a.Rs, y, x, P, sink, a.nan_to_num ? nullptr : &lp,
                                                      a.guard_verbatim != 0, gc), a.nan_to_num);
@@ -422,7 +510,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 ekf_thread_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a) {
   const long long b = (long long)blockIdx.x * BLOCK + threadIdx.x;
   if (b >= a.B) return;
-  const Segment whole = {0, a.T, true, true, nullptr, nullptr};
+  const Segment whole = {0, a.T, true, true, nullptr, nullptr, nullptr};
   ekf_trajectory<Ode, Tab, KC, LK, SQ>(a, b, whole);
 }
 
@@ -454,11 +542,30 @@ struct SchedArgs {
   const long long* last_obs; // nullable (no observations): see Segment
 };
 
-template <class Ode, class Tab, int KC, int LK, int BLOCK, int MINB, int SQ = 0>
+template <class Ode, class Tab, int KC, int LK, int BLOCK, int MINB, int SQ = 0, bool STG = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 ekf_thread_sched_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a,
                         const __grid_constant__ SchedArgs s) {
   const int lane = threadIdx.x & 31;
+  // per-warp observation ring (STG): 2 x OBS_CH x LK lines of 256 bytes + 2 mbarriers
+  constexpr int LKS = (STG && LK > 0) ? LK : 1;
+  __shared__ __align__(128) double obs_ring[STG ? BLOCK / 32 : 1][STG ? 2 * OBS_CH * LKS * 32 : 1];
+  __shared__ unsigned long long obs_bar[STG ? BLOCK / 32 : 1][2];
+  __shared__ unsigned obs_par[STG ? BLOCK / 32 : 1];
+  ObsStage stage = {nullptr, nullptr, nullptr};
+  if constexpr (STG) {
+    const int w = threadIdx.x >> 5;
+    if (lane == 0) {
+      mbar_init(&obs_bar[w][0], 1);
+      mbar_init(&obs_bar[w][1], 1);
+      obs_par[w] = 0u;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    stage.buf = obs_ring[w];
+    stage.bar = obs_bar[w];
+    stage.parity = &obs_par[w];
+  }
   const long long total = s.nblk * s.nseg;
   for (;;) {
     long long item = 0;
@@ -484,7 +591,8 @@ ekf_thread_sched_kernel(const __grid_constant__ EkfArgs<Ode::NX, Ode::NP> a,
       sg.last = seg + 1 == s.nseg;
       sg.ws = s.ws;
       sg.last_obs = s.last_obs;
-      ekf_trajectory<Ode, Tab, KC, LK, SQ>(a, b, sg);
+      sg.stg = STG ? &stage : nullptr;
+      ekf_trajectory<Ode, Tab, KC, LK, SQ, STG>(a, b, sg);
     }
     __threadfence();
     __syncwarp();

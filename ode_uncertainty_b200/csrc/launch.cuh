@@ -201,6 +201,16 @@ int launch_ekf_variant(const EkfArgs<Ode::NX, Ode::NP>& a, const odeu_ekf_io& io
     static const int cap = getenv("ODEU_SCHED_CAP") ? atoi(getenv("ODEU_SCHED_CAP")) : 1;       // tuning knob
     const long long useful = (g.nblk * 32 + Cfg::BLOCK - 1) / Cfg::BLOCK;  // more warps than blocks only spin
     if (cap && resident > useful) resident = useful;
+    // per-trajectory observation streams are staged through shared memory by bulk-async copies
+    // (whole 256-byte lines per warp: B % 32 == 0; ODEU_NO_OBS_STAGE=1 keeps the plain loads, for A/B runs)
+    if constexpr (LK > 0) {
+      static const bool no_stage = getenv("ODEU_NO_OBS_STAGE") != nullptr;
+      if (a.ys_per_traj && a.B % 32 == 0 && !no_stage) {
+        ekf_thread_sched_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB, SQ, true>
+            <<<(unsigned)resident, Cfg::BLOCK, 0, stream>>>(a, s);
+        return 0;
+      }
+    }
     ekf_thread_sched_kernel<Ode, Tab, Cfg::KC, LK, Cfg::BLOCK, Cfg::MINB, SQ>
         <<<(unsigned)resident, Cfg::BLOCK, 0, stream>>>(a, s);
     return 0;

@@ -162,12 +162,12 @@ int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
     for (long long seg = 0; seg < nseg; ++seg)
       for (long long b = 0; b < io.B; ++b) {
         Segment sg = {seg * seg_len, (seg + 1 == nseg) ? (long long)io.T : (seg + 1) * seg_len, seg == 0,
-                      seg + 1 == nseg, (double*)io.workspace, nullptr};
+                      seg + 1 == nseg, (double*)io.workspace, nullptr, nullptr};
         run(b, sg);
       }
     return 0;
   }
-  const Segment whole = {0, (long long)io.T, true, true, nullptr, nullptr};
+  const Segment whole = {0, (long long)io.T, true, true, nullptr, nullptr, nullptr};
   for (long long b = 0; b < io.B; ++b) run(b, whole);
   return 0;
 }

@@ -93,3 +93,37 @@ def test_dense_path_per_trajectory_observations():
         one = ekf_dense_run(plan, t(x0[b:b + 1]), m["T"], ys=t(ys[:, b]), **kw)
         assert torch.equal(r.nll[b], one.nll[0]) and torch.equal(r.xT[b], one.xT[0]) and torch.equal(r.PT[b], one.PT[0])
     # (Oracle-B holds n <= 16 states; the single-sequence reference-code fixture pins this path: tests/test_dense.py)
+
+
+@pytest.mark.parametrize("guard", ["intended", "reference"])
+def test_bulk_async_staged_observation_stream_equals_plain_loads(guard):
+    """At benchmark batch sizes (B % 32 == 0, dynamic scheduler) the per-trajectory observation stream is
+    staged through shared memory with cp.async.bulk + mbarrier (ekf_thread.cuh, OBS_CH steps per chunk).  A
+    subset of the same trajectories run alone (B = 70: static launch, plain global loads) must give the
+    same bits - with observations at every step, and with gaps (every third step, stopping early) so that
+    chunks hold between 0 and OBS_CH lines and segment ends fall inside a chunk."""
+    from ode_uncertainty_b200 import Plan, ekf_run, _native as N
+    dev = torch.device("cuda:0")
+    B, T, n = 32768, 333, 3
+    rng = np.random.default_rng(12)
+    x0 = torch.tensor(1.0 + rng.uniform(-1, 1, (B, n)), device=dev)
+    plan = Plan(ode_id=N.ODE_LORENZ, solver_id=N.SOLVER_RKF45, step_size=0.01)
+    assert N.lib().odeu_ekf_workspace_bytes(plan.handle, B, T) > 0
+    for pattern in ("all", "gaps"):
+        flags = torch.ones(T, dtype=torch.uint8, device=dev)
+        if pattern == "gaps":
+            flags.zero_()
+            flags[2:int(0.7 * T):3] = 1
+        n_obs = int(flags.sum())
+        ymap = torch.zeros(T, dtype=torch.int64, device=dev)
+        ymap[flags.bool()] = torch.arange(n_obs, device=dev)
+        gen = torch.Generator(device=dev); gen.manual_seed(3)
+        ys = 1.0 + 0.3 * torch.randn((n_obs, B, n), generator=gen, dtype=torch.float64, device=dev)
+        kw = dict(P0_sqrt=np.eye(n) * 0.5, H=np.eye(n), R_sqrt=np.eye(n) * 0.1, correct_flags=flags, xy_index_map=ymap, guard=guard)
+        big = ekf_run(plan, x0, T, ys=ys, ys_per_trajectory=True, **kw)
+        idx = torch.tensor([0, 1, 31, 32, 33, 1000, 4097, 20000, B - 33, B - 1] + list(range(5000, 5060)), device=dev)
+        small = ekf_run(plan, x0[idx], T, ys=ys[:, idx].contiguous(), ys_per_trajectory=True, **kw)
+        for k in ("xT", "PT", "epsT", "yhatT", "ST"):
+            assert torch.equal(getattr(big, k)[idx], getattr(small, k)), (pattern, k)
+        assert torch.allclose(big.nll[idx], small.nll, rtol=1e-12, atol=1e-12)     # (log-determinant flushed per time segment)
+        assert torch.isfinite(big.nll).all()

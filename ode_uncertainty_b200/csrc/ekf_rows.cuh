@@ -100,22 +100,47 @@ void fill_rows_schedule(GradArgs<NXA, NPA>& a) {
 // Shared-memory map (units of S).  DF, P and the stage tangents use a PAIRED layout when S is a
 // plain double: elements 2e, 2e+1 of one trajectory are adjacent, so one LDS.128 fetches two
 // operands ([e/2][TB][2]); otherwise [e][TB].  X, TH and the measurement exchange are [e][TB].
+// smallest stride >= base, multiple of align, with mult * stride = gp (mod bankrow); gp = 0: no padding
+constexpr int rows_pad_stride(int base, int mult, int align, int gp, int bankrow) {
+  int best = base;
+  for (int st = (base + align - 1) / align * align; gp != 0 && st < base + 2 * bankrow; st += align)
+    if ((mult * st) % bankrow == gp) { best = st; break; }
+  return best;
+}
+
 template <class Ode, class Tab, class S, int TB>
 struct RowsSmem {
   static constexpr int n = Ode::NX;
   static constexpr int NP2 = n + (n & 1);              // padded leading dimension (even)
   static constexpr int NSLOT = TanSched<Tab>::NSLOT;
-  static constexpr int EXN = 3 * n * ROWS_LMAX;
-  static constexpr int MAT = n * NP2;
+  static constexpr int PRS = sizeof(S) == 8 ? 2 : 1;   // elements per 16 bytes (paired layout)
+  // Bank placement of the row groups.  The lanes of one trajectory's G row groups are neighbours (see the kernel),
+  // so a quarter warp holds 8 / G trajectories (x 16 bytes = 128 / G bytes of banks) times G groups: an access
+  // whose address depends on the thread's own row r = g Q + q is conflict free when the group step moves it by
+  // GP = 128 / G bytes (mod 128).  The strides below are padded accordingly (Q entries apart = one group apart);
+  // without it every own-row / own-column access is a 2-way conflict (ncu: LDS.128 8 wavefronts instead of 4).
+  static constexpr int G = Ode::ROW_GROUPS;
+  static constexpr int Q = Ode::ROW_CLASSES;
+  static constexpr int BANKROW = 128 / (int)sizeof(S);
+  static constexpr int GP = (G > 1 && BANKROW % G == 0) ? BANKROW / G : 0;
+  static constexpr int pad_stride(int base, int mult, int align) { return rows_pad_stride(base, mult, align, GP, BANKROW); }
+  static constexpr int CS = pad_stride(NP2 * TB, Q, PRS);      // column stride of P and of the stage tangents
+  static constexpr int XS = pad_stride(TB, Q, 1);              // entry stride of the stage state
+  static constexpr int TS = TB;                                // entry stride of the parameters (not padded: the 2-way
+                                                               // conflict of the few parameter reads is cheaper than
+                                                               // losing the second CTA per SM to 240 doubles)
+  static constexpr int RS = pad_stride(ROWS_LMAX * TB, Q, 1);  // row stride of the measurement exchange
+  static constexpr int EXN = 3 * n * RS;
+  static constexpr int MAT = n * CS;
   static constexpr bool EX_ALIAS = NSLOT >= 2 && MAT >= EXN;
   static constexpr int DFN = ((Ode::NNZ > n ? Ode::NNZ : n) + 1) / 2 * 2;
   static constexpr int o_th = 0;
-  static constexpr int o_x = o_th + (Ode::NP + (Ode::NP & 1)) * TB;
-  static constexpr int o_df = o_x + NP2 * TB;
-  static constexpr int o_p = o_df + DFN * TB;
-  static constexpr int o_ks = o_p + MAT * TB;
-  static constexpr int o_ex = EX_ALIAS ? o_ks + MAT * TB : o_ks + NSLOT * MAT * TB;
-  static constexpr int total = EX_ALIAS ? o_ks + NSLOT * MAT * TB : o_ex + EXN * TB;
+  static constexpr int o_x = o_th + (Ode::NP + (Ode::NP & 1)) * TS;
+  static constexpr int o_df = o_x + NP2 * XS;
+  static constexpr int o_p = o_df + DFN * TB + (G - 1) * GP;
+  static constexpr int o_ks = o_p + MAT;
+  static constexpr int o_ex = EX_ALIAS ? o_ks + MAT : o_ks + NSLOT * MAT;
+  static constexpr int total = EX_ALIAS ? o_ks + NSLOT * MAT : o_ex + EXN;
   static constexpr size_t bytes = (size_t)total * sizeof(S);
 };
 
@@ -131,7 +156,7 @@ struct RowThread {
   using Args = GradArgs<Ode::NX, Ode::NP>;
   using SM = RowsSmem<Ode, Tab, S, TB>;
   static constexpr int NP2 = SM::NP2;
-  static constexpr int MAT = SM::MAT;
+  static constexpr int CS = SM::CS, XS = SM::XS, TS = SM::TS, RS = SM::RS, GP = SM::GP;
   static_assert(Q * G == n, "rows = groups x classes");
 
   // ---- per-thread state
@@ -174,10 +199,10 @@ struct RowThread {
   ODEU_HD S* Xp(S* sm) const { return bl(sm) + SM::o_x; }
   ODEU_HD S* THp(S* sm) const { return bl(sm) + SM::o_th; }
   ODEU_HD S* DFp(S* sm) const { return bp(sm) + SM::o_df; }
-  ODEU_HD S* Prow(S* sm, int j) const { return bp(sm) + SM::o_p + j * (NP2 * TB); }        // + pe(k)
-  ODEU_HD S* Kcol(S* sm, int slot, int c) const { return bp(sm) + SM::o_ks + (slot * n + c) * (NP2 * TB); }  // + pe(m)
+  ODEU_HD S* Prow(S* sm, int j) const { return bp(sm) + SM::o_p + j * CS; }        // + pe(k)
+  ODEU_HD S* Kcol(S* sm, int slot, int c) const { return bp(sm) + SM::o_ks + (slot * n + c) * CS; }  // + pe(m)
   ODEU_HD S& EX(S* sm, int which, int i, int l) const {
-    return bl(sm)[SM::o_ex + ((which * n + i) * LM + l) * TB];
+    return bl(sm)[SM::o_ex + (which * n + i) * RS + l * TB];
   }
 
   // `unit` = first unit of this lane slot; a scalar with NL lanes also carries unit + TB, ...
@@ -203,7 +228,7 @@ struct RowThread {
 #pragma unroll
       for (int u = 0; u < NL; ++u) lane_set(v, u, a.theta ? a.theta[k * a.B + b[u]] : a.theta_shared[k]);
       seed_theta(a, k, v);
-      THp(sm)[k * TB] = v;
+      THp(sm)[k * TS] = v;
     }
     seed_x0(a);
     for (int k = 0; k < NP2; ++k) {
@@ -246,7 +271,7 @@ struct RowThread {
         }
         if (!first) xi = x + s * a.h;
       }
-      Xp(sm)[r * TB] = xi;
+      Xp(sm)[r * XS] = xi;
     }
   }
   ODEU_HD void stage_a_rt(const Args& a, int i, S* sm) {
@@ -264,10 +289,10 @@ struct RowThread {
   // ---- interval B: equation r and its partials at the stage state (one copy of the code)
   ODEU_HD void stage_b(const Args& a, int i, S* sm) {
     S f, df[Q + 2];
-    Ode::template row<S>(q, g, t + a.h * a.rt_c[i], Xp(sm), TB, THp(sm), TB, f, df);
+    Ode::template row<S>(q, g, t + a.h * a.rt_c[i], Xp(sm), XS, THp(sm), TS, f, df);
     fcur = f;
     if (a.rw_need[i]) {
-      S* d = DFp(sm) + Ode::row_off(g, q) * TB;     // row offsets are even
+      S* d = DFp(sm) + Ode::row_off(g, q) * TB + g * GP;     // row offsets are even; group g shifted by g GP
       const int nd = Ode::row_ndep(q);
 #pragma unroll
       for (int k = 0; k < Q + 2; ++k)
@@ -323,12 +348,12 @@ struct RowThread {
 #pragma unroll
           for (int k = 0; k + 1 < nd; k += 2) {
             S u, v;
-            ld2(d + pe(off + k), u, v);
+            ld2(d + pe(off + k) + gm * GP, u, v);
             const S term = u * W[Ode::row_dep(gm, qm, k)] + v * W[Ode::row_dep(gm, qm, k + 1)];
             s = (k == 0) ? term : s + term;
           }
           if (nd & 1) {
-            const S term = d[pe(off + nd - 1)] * W[Ode::row_dep(gm, qm, nd - 1)];
+            const S term = d[pe(off + nd - 1) + gm * GP] * W[Ode::row_dep(gm, qm, nd - 1)];
             s = (nd == 1) ? term : s + term;
           }
           acc[gm * Q + qm] = s;
@@ -377,7 +402,7 @@ struct RowThread {
     epsr = d_abs(x0 - x1);
     x = x1;
     t = t + a.h;
-    Xp(sm)[r * TB] = x;
+    Xp(sm)[r * XS] = x;
   }
   // ---- row r of M = J P, then of P+ = M J^T + Q        (J(k, j) = Kcol(0, j)[k])
   ODEU_HD void phase_mp(const Args& a, S* sm) {
@@ -499,7 +524,7 @@ struct RowThread {
       if (l < L) {
         if (a.h_sel_all) {     // H row l = unit vector: y_hat_l = x[h_l], S_lm = (P H^T)[h_l][m] + R_lm
           const int hl = a.h_sel[l];
-          dvec[l] = y[l] - xs[hl * TB];
+          dvec[l] = y[l] - xs[hl * XS];
 #pragma unroll
           for (int m = 0; m < LM; ++m) {
             if (m <= l) {
@@ -511,7 +536,7 @@ struct RowThread {
         } else {
           S s = xs[0] * a.H[l * n];
 #pragma unroll
-          for (int j = 1; j < n; ++j) s = s + xs[j * TB] * a.H[l * n + j];
+          for (int j = 1; j < n; ++j) s = s + xs[j * XS] * a.H[l * n + j];
           dvec[l] = y[l] - s;
 #pragma unroll
           for (int m = 0; m < LM; ++m) {
@@ -607,10 +632,10 @@ struct RowThread {
       const bool to_slot = a.save_interval > 0 && next_save <= a.T;
       for (int l = 0; l < L; ++l) {
         double yh;
-        if (a.h_sel_all) yh = lane_get(xs[a.h_sel[l] * TB], 0);
+        if (a.h_sel_all) yh = lane_get(xs[a.h_sel[l] * XS], 0);
         else {
           yh = lane_get(xs[0], 0) * a.H[l * n];
-          for (int j = 1; j < n; ++j) yh = yh + lane_get(xs[j * TB], 0) * a.H[l * n + j];
+          for (int j = 1; j < n; ++j) yh = yh + lane_get(xs[j * XS], 0) * a.H[l * n + j];
         }
         if (to_slot && a.out_yhat) a.out_yhat[(slot * L + l) * a.B + b[0]] = yh;
         if (a.yhatT) a.yhatT[l * a.B + b[0]] = yh;
@@ -715,7 +740,11 @@ ekf_rows_kernel(const __grid_constant__ GradArgs<Ode::NX, Ode::NP> a, double* PT
   RowThread<Ode, Tab, S, TB, LT> th;
   const int lane = threadIdx.x & 31;
   constexpr int NL = lanes_of<S>::value;
-  th.init(a, (long long)blockIdx.x * (TB * NL) + lane % TB, lane % TB, lane / TB, threadIdx.x >> 5, sm);
+  // lanes G t .. G t + G - 1 = the row groups of trajectory t: the lanes that read the SAME Jacobian / covariance
+  // entries sit next to each other, where the shared-memory pipe merges them into one wavefront (+6 % at C3
+  // against the group-major order lane = g * TB + t)
+  constexpr int GR = Ode::ROW_GROUPS;
+  th.init(a, (long long)blockIdx.x * (TB * NL) + lane / GR, lane / GR, lane % GR, threadIdx.x >> 5, sm);
   __syncthreads();
   th.save_initial(a, sm);
   for (long long step = 0; step < a.T; ++step) {

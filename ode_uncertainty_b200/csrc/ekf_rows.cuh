@@ -349,12 +349,12 @@ struct RowThread {
           for (int k = 0; k + 1 < nd; k += 2) {
             S u, v;
             ld2(d + pe(off + k) + gm * GP, u, v);
-            const S term = u * W[Ode::row_dep(gm, qm, k)] + v * W[Ode::row_dep(gm, qm, k + 1)];
-            s = (k == 0) ? term : s + term;
+            s = (k == 0) ? d_fma(v, W[Ode::row_dep(gm, qm, k + 1)], u * W[Ode::row_dep(gm, qm, k)])
+                         : d_fma(v, W[Ode::row_dep(gm, qm, k + 1)], d_fma(u, W[Ode::row_dep(gm, qm, k)], s));
           }
           if (nd & 1) {
-            const S term = d[pe(off + nd - 1) + gm * GP] * W[Ode::row_dep(gm, qm, nd - 1)];
-            s = (nd == 1) ? term : s + term;
+            s = (nd == 1) ? d[pe(off + nd - 1) + gm * GP] * W[Ode::row_dep(gm, qm, nd - 1)]
+                          : d_fma(d[pe(off + nd - 1) + gm * GP], W[Ode::row_dep(gm, qm, nd - 1)], s);
           }
           acc[gm * Q + qm] = s;
         }
@@ -417,12 +417,12 @@ struct RowThread {
       for (int k = 0; k + 1 < n; k += 2) {
         S u, v;
         ld2(pj + pe(k), u, v);
-        M[k] = (j == 0) ? Jr[j] * u : M[k] + Jr[j] * u;
-        M[k + 1] = (j == 0) ? Jr[j] * v : M[k + 1] + Jr[j] * v;
+        M[k] = (j == 0) ? Jr[j] * u : d_fma(Jr[j], u, M[k]);
+        M[k + 1] = (j == 0) ? Jr[j] * v : d_fma(Jr[j], v, M[k + 1]);
       }
       if constexpr (n & 1) {
         const S u = pj[pe(n - 1)];
-        M[n - 1] = (j == 0) ? Jr[j] * u : M[n - 1] + Jr[j] * u;
+        M[n - 1] = (j == 0) ? Jr[j] * u : d_fma(Jr[j], u, M[n - 1]);
       }
     }
 #pragma unroll
@@ -432,12 +432,12 @@ struct RowThread {
       for (int k = 0; k + 1 < n; k += 2) {
         S u, v;
         ld2(kj + pe(k), u, v);
-        W[k] = (j == 0) ? M[j] * u : W[k] + M[j] * u;
-        W[k + 1] = (j == 0) ? M[j] * v : W[k + 1] + M[j] * v;
+        W[k] = (j == 0) ? M[j] * u : d_fma(M[j], u, W[k]);
+        W[k + 1] = (j == 0) ? M[j] * v : d_fma(M[j], v, W[k + 1]);
       }
       if constexpr (n & 1) {
         const S u = kj[pe(n - 1)];
-        W[n - 1] = (j == 0) ? M[j] * u : W[n - 1] + M[j] * u;
+        W[n - 1] = (j == 0) ? M[j] * u : d_fma(M[j], u, W[n - 1]);
       }
     }
     // process noise (src/filters/sqrt_ekf.py:96-136), row r
@@ -698,9 +698,10 @@ struct RowThread {
 #pragma unroll
     for (int l = 0; l < LM; ++l) {
       if (l < L) {
-        x = x + Krow[l] * dvec[l];
+        x = d_fma(Krow[l], dvec[l], x);
+        const S nk = -Krow[l], ng = -ph[l];
 #pragma unroll
-        for (int k = 0; k < n; ++k) W[k] = W[k] - Krow[l] * EX(sm, 0, k, l) - ph[l] * EX(sm, 1, k, l);
+        for (int k = 0; k < n; ++k) W[k] = d_fma(ng, EX(sm, 1, k, l), d_fma(nk, EX(sm, 0, k, l), W[k]));
       }
     }
   }

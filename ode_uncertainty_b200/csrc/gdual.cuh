@@ -135,6 +135,16 @@ template <class S, int K, ODEU_NOT_DOUBLE(S)> ODEU_HD GDual<S, K> operator/(doub
   return r;
 }
 
+// ---- fused multiply-add a b + c: value 1 FMA, each direction 2 FMAs (the operator form a * b + c costs
+// MUL + FMA + ADD per direction, because the sum of the two cross terms cannot be re-associated into c)
+ODEU_HD double d_fma(double a, double b, double c) { return fma(a, b, c); }
+template <class S, int K> ODEU_HD GDual<S, K> d_fma(const GDual<S, K>& a, const GDual<S, K>& b, const GDual<S, K>& c) {
+  GDual<S, K> r; r.v = d_fma(a.v, b.v, c.v);
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.d[k] = d_fma(a.v, b.d[k], d_fma(a.d[k], b.v, c.d[k]));
+  return r;
+}
+
 // ---- elementary functions (recursive in the component type)
 template <class S, int K> ODEU_HD GDual<S, K> d_exp(const GDual<S, K>& a) {
   GDual<S, K> r; r.v = d_exp(a.v);

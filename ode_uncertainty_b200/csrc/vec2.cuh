@@ -32,6 +32,7 @@ ODEU_HD V2d operator/(double x, const V2d& y) { return V2d(x / y.a, x / y.b); }
 ODEU_HD V2d d_exp(const V2d& x) { return V2d(exp(x.a), exp(x.b)); }
 ODEU_HD V2d d_sqrt(const V2d& x) { return V2d(sqrt(x.a), sqrt(x.b)); }
 ODEU_HD V2d d_rsqrt(const V2d& x) { return V2d(rsqrt_pos(x.a), rsqrt_pos(x.b)); }
+ODEU_HD V2d d_fma(const V2d& x, const V2d& y, const V2d& z) { return V2d(fma(x.a, y.a, z.a), fma(x.b, y.b, z.b)); }
 ODEU_HD V2d d_log(const V2d& x) { return V2d(log(x.a), log(x.b)); }
 ODEU_HD V2d d_abs(const V2d& x) { return V2d(fabs(x.a), fabs(x.b)); }
 

@@ -4,4 +4,6 @@ echo "== new"; timeout 300 python tools/bench_c3.py 4096 1000 2>&1 | tail -1
 echo "== base"; ODEU_LIB=build/ab/libodeu_base.so timeout 300 python tools/bench_c3.py 4096 1000 2>&1 | tail -1
 echo "== new grad"; timeout 300 python tools/bench_c3.py 4096 200 --grad 2>&1 | tail -2
 echo "== base grad"; ODEU_LIB=build/ab/libodeu_base.so timeout 300 python tools/bench_c3.py 4096 200 --grad 2>&1 | tail -2
-TAG=rows7 bash tools/r2_gpujob6.sh > /dev/null 2>&1
+echo "== new single"; timeout 300 python tools/bench_c3.py 4096 1000 --single 2>&1 | tail -1
+echo "== new single grad"; timeout 300 python tools/bench_c3.py 4096 200 --single --grad 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_grad.py tests/test_per_trajectory_obs.py tests/test_estimation.py tests/test_baseline_loss.py -m gpu -x -q 2>&1 | tail -3

@@ -560,8 +560,9 @@ struct RowThread {
 #pragma unroll
         for (int k = 0; k < LM; ++k) if (k < j) s = s - Ls[j][k] * Ls[j][k];
         inv[j] = d_rsqrt(s);                 // one MUFU + 5 DFMA instead of sqrt + division (~55 instructions,
-        const S dj = s * inv[j];             // evaluated redundantly by every row thread)
-        Ls[j][j] = dj;
+        const Mask2 z0 = mask_zero(s);       // evaluated redundantly by every row thread).  An exactly singular S
+        const S dj = zero_where(z0, s * inv[j]);   // (pivot == 0) gives a zero pivot and a zero column, not
+        Ls[j][j] = dj;                             // 0 * inf: the guard below then trips like sqrt_ekf.py:351-353
         mask_and_tiny(all_tiny, dj);
 #pragma unroll
         for (int i = 0; i < LM; ++i) {
@@ -569,7 +570,7 @@ struct RowThread {
             S v = Sm[i][j];
 #pragma unroll
             for (int k = 0; k < LM; ++k) if (k < j) v = v - Ls[i][k] * Ls[j][k];
-            v = v * inv[j];
+            v = zero_where(z0, v * inv[j]);
             Ls[i][j] = v;
             mask_and_tiny(all_tiny, v);
           }

@@ -56,6 +56,10 @@ ODEU_HD void mask_and_tiny(Mask2& k, const V2d& s) {
   k.m[1] = k.m[1] && (fabs(s.b) < 1e-16);
 }
 template <class T, int K> ODEU_HD void mask_and_tiny(Mask2& k, const GDual<T, K>& s) { mask_and_tiny(k, s.v); }
+// per-lane "exactly zero" (an exactly singular innovation: pivot 0, column 0 instead of 0 * inf)
+ODEU_HD Mask2 mask_zero(double s) { Mask2 r; r.m[0] = r.m[1] = (s == 0.0); return r; }
+ODEU_HD Mask2 mask_zero(const V2d& s) { Mask2 r; r.m[0] = (s.a == 0.0); r.m[1] = (s.b == 0.0); return r; }
+template <class T, int K> ODEU_HD Mask2 mask_zero(const GDual<T, K>& s) { return mask_zero(s.v); }
 ODEU_HD double zero_where(const Mask2& k, double s) { return k.m[0] ? 0.0 : s; }
 ODEU_HD V2d zero_where(const Mask2& k, const V2d& s) { return V2d(k.m[0] ? 0.0 : s.a, k.m[1] ? 0.0 : s.b); }
 template <class T, int K> ODEU_HD GDual<T, K> zero_where(const Mask2& k, const GDual<T, K>& s) {

@@ -175,6 +175,26 @@ def test_exactly_singular_innovation_trips_the_guard(L):
     np.testing.assert_array_equal(out["xT"], free["xT"])
 
 
+
+def test_exactly_singular_innovation_on_the_row_kernel():
+    """Same degenerate update on the Hodgkin-Huxley row kernel (ekf_rows.cuh, n = 7, L = 1): P0 = 0, R = 0,
+    no process noise.  rsqrt(0) used to poison x and P there (advisor, round 1: "apply the same check to
+    the rows and grad variants"); now the pivot and its column are zero, the guard trips, K = 0 and the
+    state equals the prediction-only run bit for bit."""
+    from ode_uncertainty_b200 import Plan, _native as N
+    from ode_uncertainty_b200 import ode as O
+    ob = O.HodgkinHuxley(model="reduced-1")
+    plan = Plan(N.ODE_HODGKIN_HUXLEY, N.SOLVER_RKF45, 0.01, ode_variant=1, disable_cov_update=True)
+    n, T = plan.n, 4
+    x0 = np.repeat(ob.build_initial_value(np.array([[-70.0]]), ob.params).reshape(1, -1), 3, axis=0)
+    H = np.zeros((1, n)); H[0, 0] = 1.0
+    kw = dict(P0_sqrt=np.zeros((n, n)), H=H, R_sqrt=np.zeros((1, 1)), ys=np.full((T, 1), -60.0),
+              correct_flags=np.ones(T, np.uint8), xy_index_map=np.arange(T, dtype=np.int64))
+    free = U.run_ekf("hostemu", plan, x0, T, minimal=True, P0_sqrt=np.zeros((n, n)))
+    out = U.run_ekf("hostemu", plan, x0, T, minimal=True, **kw)
+    np.testing.assert_array_equal(out["xT"], free["xT"])
+    np.testing.assert_array_equal(out["PT"], np.zeros((3, n, n)))
+
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SMALL)

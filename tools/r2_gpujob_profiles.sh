@@ -18,5 +18,12 @@ done
 ncu --set full --clock-control none --import-source on -k regex:ekf_thread_sched_kernel -s 1 -c 1 -f -o gpurun_out/r2_Lorenz_sched_intended python tools/profile_c2.py 10000 Lorenz --guard=intended > gpurun_out/r2_ncu_Lorenz_intended.log 2>&1
 ncu -i gpurun_out/r2_Lorenz_sched_intended.ncu-rep --page raw --csv > gpurun_out/r2_Lorenz_sched_intended_raw.csv 2>/dev/null
 python tools/ncu_summary.py gpurun_out/r2_Lorenz_sched_intended_raw.csv gpurun_out/r2_Lorenz_sched_intended_ncu_full.csv
+# C3 row kernels (loss, loss + gradient): full capture + source-level shared-memory wavefront table
+TAG=r2_c3_rows GRAD=1 bash tools/r2_gpujob6.sh > /dev/null 2>&1
+for k in nll grad; do
+  python tools/ncu_summary.py gpurun_out/r2_c3_rows_${k}_raw.csv gpurun_out/r2_c3_rows_${k}_ncu_full.csv
+  python tools/ncu_lds.py gpurun_out/r2_c3_rows_${k}_source.csv > gpurun_out/r2_c3_rows_${k}_lds.txt
+done
+rm -f gpurun_out/r2_c3_rows_*_source.csv
 rm -f gpurun_out/*_raw.csv gpurun_out/*.ncu-rep      # (the reports are 34 MB each: gpurun returns at most 64 MiB)
 ls -la gpurun_out | tail -n 14

@@ -202,6 +202,14 @@ int odeu_pf_normalize(int64_t M, int64_t M_total, int32_t n, int32_t G, const do
 int odeu_pf_resample(int64_t M, int64_t M_total, int64_t slot_lo, int32_t n, double u0,
                      const double* stats_dev, const double* cdf_dev, const double* pack_dev,
                      double* x_new_dev, double* logw_dev, void* cuda_stream);
+/* The last two steps in one call: inclusive cumulative sum of the gathered weights (read straight off the packed
+ * rows) into scan scratch (odeu_pf_scan_bytes(M_total) bytes) + odeu_pf_resample; when the device-side decision
+ * is "keep", x_old [n][M] is carried over into x_new, so the caller alternates two ensemble buffers. */
+int64_t odeu_pf_scan_bytes(int64_t M_total);
+int odeu_pf_scan_resample(int64_t M, int64_t M_total, int64_t slot_lo, int32_t n, double u0,
+                          const double* stats_dev, const double* pack_dev, const double* x_old_dev,
+                          double* x_new_dev, double* logw_dev, void* scan_dev, int64_t scan_bytes,
+                          void* cuda_stream);
 
 /* NLL and its parameter gradient for B parameter sets: replaces jax.value_and_grad(nll) as the
  * optimiser calls it (scripts/run_parameter_estimation.py:599, nll :685-796).  Forward-mode

@@ -2,6 +2,10 @@
 // has no weights, no correct step and no resampling - src/filters/particle_filter.py:24-118,
 // SURVEY F5 - so this step has no reference oracle; BASELINE config 4 names it).
 //   logw_m += log N(y; H x_m, R) = -0.5 d^T R^-1 d - 0.5 log det(2 pi R),  d = y - H x_m
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
 #include "plan.h"
 
 namespace odeu {
@@ -236,6 +240,38 @@ __global__ void __launch_bounds__(256) pf_resample_kernel(const __grid_constant_
   a.logw[j] = -log((double)a.M_total);
 }
 
+// resampling fused with the "keep" branch: no copy of the ensemble is needed on the host side
+struct PfResample2Args {
+  PfResampleArgs r;
+  const double* x_old;     // [n][M] (the prediction's output)
+};
+__global__ void __launch_bounds__(256) pf_resample_or_keep_kernel(const __grid_constant__ PfResample2Args b) {
+  const PfResampleArgs& a = b.r;
+  const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (j >= a.M) return;
+  if (a.stats[2] == 0.0) {                             // device-side decision: ESS high enough, keep everything
+    for (int i = 0; i < a.n; ++i) a.x_new[i * a.M + j] = b.x_old[i * a.M + j];
+    return;
+  }
+  const double total = a.cdf[a.M_total - 1];
+  const double u = ((double)(a.slot_lo + j) + a.u0) / (double)a.M_total * total;
+  long long lo = 0, hi = a.M_total - 1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (a.cdf[mid] >= u) hi = mid; else lo = mid + 1;
+  }
+  const double* row = a.pack + lo * (a.n + 1);
+  for (int i = 0; i < a.n; ++i) a.x_new[i * a.M + j] = row[i];
+  a.logw[j] = -log((double)a.M_total);
+}
+// weight column of the packed rows as a scan input
+struct PackWeight {
+  const double* pack;
+  int stride;
+  __host__ __device__ double operator()(long long m) const { return pack[m * stride + stride - 1]; }
+};
+using PackWeightIt = thrust::transform_iterator<PackWeight, thrust::counting_iterator<long long>, double>;
+
 static int fill_weight_args(PfWeightArgs& a, int64_t M, int32_t n, int32_t L, const double* x_dev, const double* y_host,
                             const double* H_host, const double* R_host, double* logw_dev) {
   a.M = M; a.n = n; a.L = L; a.x = x_dev; a.logw = logw_dev;
@@ -326,5 +362,42 @@ extern "C" int odeu_pf_resample(int64_t M, int64_t M_total, int64_t slot_lo, int
   count_launch();
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("odeu_pf_resample: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
+// Inclusive cumulative sum of the gathered weights (CUB scan straight off the strided weight column of the packed
+// rows, no contiguous copy) + systematic resampling predicated on the device-side decision; when the decision is
+// "keep", x_old is carried over, so the caller ping-pongs two buffers and never copies the ensemble.
+extern "C" int64_t odeu_pf_scan_bytes(int64_t M_total) {
+  using namespace odeu;
+  size_t tmp = 0;
+  PackWeightIt it(thrust::counting_iterator<long long>(0), PackWeight{nullptr, 2});
+  cub::DeviceScan::InclusiveSum(nullptr, tmp, it, (double*)nullptr, (long long)M_total);
+  return (int64_t)(M_total * 8 + ((tmp + 255) / 256) * 256 + 256);
+}
+
+extern "C" int odeu_pf_scan_resample(int64_t M, int64_t M_total, int64_t slot_lo, int32_t n, double u0,
+                                     const double* stats_dev, const double* pack_dev, const double* x_old_dev,
+                                     double* x_new_dev, double* logw_dev, void* scan_dev, int64_t scan_bytes,
+                                     void* cuda_stream) {
+  using namespace odeu;
+  if (M <= 0 || M_total < M || n <= 0 || n > 16 || !stats_dev || !pack_dev || !x_old_dev || !x_new_dev || !logw_dev ||
+      !scan_dev || scan_bytes < odeu_pf_scan_bytes(M_total)) {
+    set_error("odeu_pf_scan_resample: invalid argument (scan scratch: odeu_pf_scan_bytes(M_total) bytes)");
+    return -1;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double* cdf = (double*)scan_dev;
+  void* tmp = (char*)scan_dev + ((M_total * 8 + 255) / 256) * 256;
+  size_t tmp_bytes = (size_t)scan_bytes - (size_t)((M_total * 8 + 255) / 256) * 256;
+  PackWeightIt it(thrust::counting_iterator<long long>(0), PackWeight{pack_dev, n + 1});
+  cudaError_t err = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, it, cdf, (long long)M_total, st);
+  if (err != cudaSuccess) { set_error("odeu_pf_scan_resample: scan failed: %s", cudaGetErrorString(err)); return (int)err; }
+  count_launch();
+  PfResample2Args a = {{M, M_total, slot_lo, n, u0, stats_dev, cdf, pack_dev, x_new_dev, logw_dev}, x_old_dev};
+  pf_resample_or_keep_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(a);
+  count_launch();
+  err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("odeu_pf_scan_resample: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
   return 0;
 }

@@ -105,6 +105,13 @@ def _u0(seed: int, event: int) -> float:
     return float(g.random())
 
 
+def _u0_stream(seed: int, n_events: int) -> np.ndarray:
+    """_u0(seed, k) for k = 0 .. n_events - 1 from ONE generator (constructing a Philox bit generator costs
+    ~150 us; event k's block is the k-th block of the stream started at counter 0, bit-identical values)."""
+    g = np.random.Generator(np.random.Philox(key=int(seed) & (2 ** 64 - 1), counter=[0, 0, 0, 0]))
+    return g.random(4 * max(n_events, 1))[::4].copy()
+
+
 def bootstrap_filter(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R, *, x0_shared,
                      t0: float = 0.0, seed: int = 7, ess_frac: float = 0.5, theta_shared=None,
                      device="cuda", fused: bool = True) -> Dict[str, torch.Tensor]:
@@ -142,7 +149,7 @@ def bootstrap_filter(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R,
             x = systematic_resample(x, logw, M_total, _u0(seed, k))
             logw = torch.full((M,), -math.log(M_total), dtype=torch.float64, device=dev)
             resampled.append(k)
-    return {"x": x, "logw": logw, "ess": torch.tensor(ess_hist), "resampled": resampled,
+    return {"x": x, "logw": logw, "ess": torch.tensor(ess_hist, dtype=torch.float64), "resampled": resampled,
             "loglik": loglik, "t": t}
 
 
@@ -150,7 +157,8 @@ def _bootstrap_fused(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R,
                      theta_shared, device) -> Dict[str, torch.Tensor]:
     """Device-resident bootstrap filter.  Per observation, all on torch's current stream:
     odeu_pf_run (obs_every steps) -> odeu_pf_weight_reduce -> all-gather of G x 3 doubles ->
-    odeu_pf_normalize -> all-gather of the packed (x, w) rows -> cumsum -> odeu_pf_resample.
+    odeu_pf_normalize -> all-gather of the packed (x, w) rows -> odeu_pf_scan_resample (CUB scan of the
+    weight column + resampling): four C-ABI calls and no torch operator per observation.
     The ESS test, the resampling decision and the log-likelihood stay on the device; the host reads
     them once after the last observation.  Every rank resamples its own global slots from the SAME
     gathered CDF, so the result does not depend on the number of ranks.  Needs M_total % world == 0."""
@@ -168,45 +176,58 @@ def _bootstrap_fused(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R,
     ysh = np.ascontiguousarray(np.asarray(ys, dtype=np.float64))
     n_obs = T // obs_every
     lib = N.lib()
-    xk = torch.as_tensor(np.asarray(x0_shared, dtype=np.float64).reshape(n, 1)).to(dev).repeat(1, M).contiguous()  # [n][M]
+    # two ensemble buffers [n][M]: the prediction reads A and writes B, the resampling reads B (and the gathered
+    # rows) and writes A - also when the device-side decision is "keep" - so nothing is copied or allocated per
+    # observation, and the argument block of odeu_pf_run is built once
+    xa = torch.as_tensor(np.asarray(x0_shared, dtype=np.float64).reshape(n, 1)).to(dev).repeat(1, M).contiguous()
+    xb = torch.empty_like(xa)
     logw = torch.full((M,), -math.log(M_total), **f64)
     triple = torch.zeros(3, **f64)
-    triples = torch.zeros(ws, 3, **f64)
+    triples = torch.zeros(ws, 3, **f64) if ws > 1 else triple.reshape(1, 3)
     pack = torch.empty(M, n + 1, **f64)
     pack_all = pack if ws == 1 else torch.empty(M_total, n + 1, **f64)
     stats = torch.zeros(4, **f64)
     ess_hist = torch.zeros(max(n_obs, 1), **f64)
     flag_hist = torch.zeros(max(n_obs, 1), **f64)
     scratch = torch.zeros(int(lib.odeu_pf_reduce_scratch_bytes(M)), dtype=torch.uint8, device=dev)
+    scan_bytes = int(lib.odeu_pf_scan_bytes(M_total))
+    scan = torch.empty(scan_bytes, dtype=torch.uint8, device=dev)
     p = lambda t_: C.c_void_p(t_.data_ptr())
     hp = lambda a_: a_.ctypes.data_as(C.c_void_p)
+    ths_h = None if theta_shared is None else np.ascontiguousarray(np.asarray(theta_shared, dtype=np.float64).reshape(plan.p))
+    io = N.PfIO()
+    io.M, io.T, io.seed, io.particle_offset = M, int(obs_every), int(seed), lo
+    io.x0, io.xT = xa.data_ptr(), xb.data_ptr()
+    if ths_h is not None:
+        io.theta_shared = ths_h.ctypes.data
+    io_ref = C.byref(io)
     t = float(t0)
     h = plan.step_size
-    for k in range(n_obs):
-        r = pf_run(plan, M, obs_every, x0=xk.t(), t0=t, theta_shared=theta_shared, seed=seed,
-                   particle_offset=lo, step_offset=k * obs_every)
-        xk = r.xT.t()                                   # the kernel's own [n][M] buffer, no copy
-        for _ in range(obs_every):
-            t = t + h                                   # the kernel accumulates t the same way (rksolver.py:145)
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        yk = np.ascontiguousarray(ysh[k])
-        with torch.cuda.device(dev):
-            N.check(lib.odeu_pf_weight_reduce(M, n, L, p(xk), hp(yk), hp(Hh), hp(Rh), p(logw), p(triple), p(scratch), st),
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    pxa, pxb, plogw, ptriple, pscratch, ppack, ppack_all, pstats, pscan = (p(xa), p(xb), p(logw), p(triple), p(scratch), p(pack),
+                                                                            p(pack_all), p(stats), p(scan))
+    ptriples = p(triples)
+    u0s = _u0_stream(seed, n_obs)
+    tri_in = triple.reshape(1, 3)
+    with torch.cuda.device(dev):
+        for k in range(n_obs):
+            io.t0, io.step_offset = t, k * obs_every
+            N.check(lib.odeu_pf_run(plan.handle, io_ref, st), "odeu_pf_run")
+            for _ in range(obs_every):
+                t = t + h                               # the kernel accumulates t the same way (rksolver.py:145)
+            yk = np.ascontiguousarray(ysh[k])
+            N.check(lib.odeu_pf_weight_reduce(M, n, L, pxb, hp(yk), hp(Hh), hp(Rh), plogw, ptriple, pscratch, st),
                     "odeu_pf_weight_reduce")
             if ws > 1:
-                dist.all_gather_into_tensor(triples, triple.reshape(1, 3))
-            else:
-                triples = triple.reshape(1, 3)
-            N.check(lib.odeu_pf_normalize(M, M_total, n, ws, p(triples), p(xk), p(logw), p(pack), p(stats),
+                dist.all_gather_into_tensor(triples, tri_in)
+            N.check(lib.odeu_pf_normalize(M, M_total, n, ws, ptriples, pxb, plogw, ppack, pstats,
                                           C.c_void_p(ess_hist.data_ptr() + 8 * k), C.c_void_p(flag_hist.data_ptr() + 8 * k),
                                           float(ess_frac), st), "odeu_pf_normalize")
             if ws > 1:
                 dist.all_gather_into_tensor(pack_all, pack)
-            cdf = torch.cumsum(pack_all[:, n], 0)
-            x_new = xk.clone()                          # kept when the device-side decision says "no resampling"
-            N.check(lib.odeu_pf_resample(M, M_total, lo, n, _u0(seed, k), p(stats), p(cdf), p(pack_all), p(x_new), p(logw), st),
-                    "odeu_pf_resample")
-        xk = x_new
+            N.check(lib.odeu_pf_scan_resample(M, M_total, lo, n, float(u0s[k]), pstats, ppack_all, pxb, pxa, plogw,
+                                              pscan, scan_bytes, st), "odeu_pf_scan_resample")
+    xk = xa
     flags = flag_hist[:n_obs].cpu().numpy()             # the only device-to-host reads of the run
     return {"x": xk.t(), "logw": logw, "ess": ess_hist[:n_obs].cpu(), "resampled": [int(k) for k in np.nonzero(flags)[0]],
             "loglik": float(stats[3]), "t": t}

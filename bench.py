@@ -320,7 +320,9 @@ def _scale_extras(dev, world, rank):
         out["c4_scale"] = {"predict_particle_steps_per_s": M4 * T4 / tp, "bootstrap_particle_steps_per_s": M4 * T4 / tb,
                            "bootstrap_over_predict_time": tb / tp, "n_gpus": world, "scaling": "strong",
                            "sample": f"M={M4} particles over {world} GPU(s) x T={T4} (config: T=5000), weights every {every} steps, "
-                                     f"{len(res['resampled'])} resampling exchanges (forced), 2 all-gathers per observation, no host read",
+                                     f"{len(res['resampled'])} resampling exchanges (forced), no host read; N > 1: peer-memory path (rows and weights stay "
+                                     f"with their owner in symmetric buffers and are read over NVLink, 2 device-side barriers per observation, "
+                                     f"no NCCL on the data path; ODEU_PF_NCCL=1 selects the all-gather formulation)",
                            "predict_ms": 1e3 * tp, "bootstrap_ms": 1e3 * tb}
     return out
 

@@ -211,6 +211,29 @@ int odeu_pf_scan_resample(int64_t M, int64_t M_total, int64_t slot_lo, int32_t n
                           double* x_new_dev, double* logw_dev, void* scan_dev, int64_t scan_bytes,
                           void* cuda_stream);
 
+/* Peer-memory variant of the global steps (one process per GPU; every rank's buffers are mapped into every other
+ * rank over NVLink / NVSwitch, e.g. by torch.distributed._symmetric_memory or CUDA IPC): no collective library on
+ * the data path.  Pointer tables are HOST arrays of G device pointers (entry q = rank q's buffer), G <= 16.
+ *   odeu_pf_publish_triple      stores this rank's triple into slot `rank` of every rank's triples [G][3]
+ *   (caller: cross-rank barrier)
+ *   odeu_pf_normalize_w         odeu_pf_normalize + the weights once more as a contiguous array w [M]; pack and w
+ *                               are this rank's SYMMETRIC buffers
+ *   (caller: cross-rank barrier)
+ *   odeu_pf_scan_resample_peer  CDF scan streaming the G weight arrays from their owners (8 B per particle), then
+ *                               systematic resampling that fetches only the ancestor rows it needs from the owning
+ *                               rank (one 32-byte sector each at n = 3) - an all-gather would deliver the whole
+ *                               ensemble to every rank.  M_total = G * M. */
+int odeu_pf_publish_triple(const double* triple_dev, double* const* peer_triples_host, int32_t rank, int32_t G,
+                           void* cuda_stream);
+int odeu_pf_normalize_w(int64_t M, int64_t M_total, int32_t n, int32_t G, const double* triples_dev,
+                        const double* x_dev, double* logw_dev, double* pack_dev, double* w_dev,
+                        double* stats_dev, double* ess_hist_dev, double* flag_hist_dev, double ess_frac,
+                        void* cuda_stream);
+int odeu_pf_scan_resample_peer(int64_t M, int64_t M_total, int64_t slot_lo, int32_t n, int32_t G, double u0,
+                               const double* stats_dev, const double* const* peer_pack_host,
+                               const double* const* peer_w_host, const double* x_old_dev, double* x_new_dev,
+                               double* logw_dev, void* scan_dev, int64_t scan_bytes, void* cuda_stream);
+
 /* NLL and its parameter gradient for B parameter sets: replaces jax.value_and_grad(nll) as the
  * optimiser calls it (scripts/run_parameter_estimation.py:599, nll :685-796).  Forward-mode
  * tangents over the requested parameters (at most 32), fused with the filter loop.  Uses from

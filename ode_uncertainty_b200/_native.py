@@ -26,6 +26,7 @@ SYMBOLS = (
     "odeu_ekf_dense_run", "odeu_ekf_dense_workspace_bytes", "odeu_param_sensitivity",
     "odeu_pf_reduce_scratch_bytes", "odeu_pf_weight_reduce", "odeu_pf_normalize", "odeu_pf_resample",
     "odeu_pf_scan_bytes", "odeu_pf_scan_resample",
+    "odeu_pf_publish_triple", "odeu_pf_normalize_w", "odeu_pf_scan_resample_peer",
     "odeu_lbfgs_workspace_doubles", "odeu_lbfgs_step",
 )
 
@@ -135,6 +136,13 @@ def lib() -> C.CDLL:
     L.odeu_pf_scan_bytes.restype = C.c_int64
     L.odeu_pf_scan_resample.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_double] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
     L.odeu_pf_scan_resample.restype = C.c_int
+    L.odeu_pf_publish_triple.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.odeu_pf_publish_triple.restype = C.c_int
+    L.odeu_pf_normalize_w.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p]
+    L.odeu_pf_normalize_w.restype = C.c_int
+    L.odeu_pf_scan_resample_peer.argtypes = ([C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 7
+                                             + [C.c_int64, C.c_void_p])
+    L.odeu_pf_scan_resample_peer.restype = C.c_int
     L.odeu_lbfgs_workspace_doubles.argtypes = [C.c_int32, C.c_int32]
     L.odeu_lbfgs_workspace_doubles.restype = C.c_int64
     L.odeu_lbfgs_step.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double] + [C.c_void_p] * 6

@@ -191,6 +191,7 @@ struct PfNormArgs {
   double* ess_hist;        // this observation's slot, or null
   double* flag_hist;
   double ess_frac;
+  double* w_out;           // nullable: [M] the weights once more, contiguous (what the peers scan)
 };
 
 __global__ void __launch_bounds__(256) pf_normalize_kernel(const __grid_constant__ PfNormArgs a) {
@@ -210,7 +211,9 @@ __global__ void __launch_bounds__(256) pf_normalize_kernel(const __grid_constant
   a.logw[m] = lw;
   double* row = a.pack + m * (a.n + 1);
   for (int i = 0; i < a.n; ++i) row[i] = a.x[i * a.M + m];
-  row[a.n] = exp(lw);
+  const double w = exp(lw);
+  row[a.n] = w;
+  if (a.w_out) a.w_out[m] = w;
 }
 
 struct PfResampleArgs {
@@ -271,6 +274,66 @@ struct PackWeight {
   __host__ __device__ double operator()(long long m) const { return pack[m * stride + stride - 1]; }
 };
 using PackWeightIt = thrust::transform_iterator<PackWeight, thrust::counting_iterator<long long>, double>;
+
+// ---- peer-memory variant (one process per GPU, buffers mapped into every rank over NVLink / NVSwitch):
+// no collective library on the data path.  Each rank keeps its packed rows and weights in its own symmetric
+// buffer; the peers read them in place - the CDF scan streams the G weight arrays (8 bytes per particle), the
+// resampling fetches ONLY the ancestor rows it needs (one 32-byte sector each at n = 3) - instead of every rank
+// receiving the whole ensemble in an all-gather.
+constexpr int PF_MAX_PEERS = 16;
+struct PfPeers {
+  const double* pack[PF_MAX_PEERS];   // rank q's packed rows [M][n + 1]
+  const double* w[PF_MAX_PEERS];      // rank q's weights [M]
+};
+struct PfPublishArgs {
+  const double* triple;               // this rank's (max, sum, sum of squares)
+  double* dst[PF_MAX_PEERS];          // rank q's triples array [G][3]
+  int rank, G;
+};
+__global__ void pf_publish_triple_kernel(const __grid_constant__ PfPublishArgs a) {
+  const int q = threadIdx.x / 3, c = threadIdx.x % 3;
+  if (q < a.G) a.dst[q][3 * a.rank + c] = a.triple[c];      // remote stores; the barrier that follows orders them
+}
+struct PeerWeight {                   // global particle index -> weight, read from the owning rank
+  PfPeers p;
+  long long M;
+  __device__ double operator()(long long m) const {
+    const int q = (int)(m / M);
+    return p.w[q][m - (long long)q * M];
+  }
+};
+using PeerWeightIt = thrust::transform_iterator<PeerWeight, thrust::counting_iterator<long long>, double>;
+struct PfResamplePeerArgs {
+  PfResampleArgs r;                   // (r.pack unused)
+  const double* x_old;
+  PfPeers p;
+};
+__global__ void __launch_bounds__(256) pf_resample_peer_kernel(const __grid_constant__ PfResamplePeerArgs b) {
+  const PfResampleArgs& a = b.r;
+  const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (j >= a.M) return;
+  if (a.stats[2] == 0.0) {
+    for (int i = 0; i < a.n; ++i) a.x_new[i * a.M + j] = b.x_old[i * a.M + j];
+    return;
+  }
+  const double total = a.cdf[a.M_total - 1];
+  const double u = ((double)(a.slot_lo + j) + a.u0) / (double)a.M_total * total;
+  long long lo = 0, hi = a.M_total - 1;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (a.cdf[mid] >= u) hi = mid; else lo = mid + 1;
+  }
+  const int q = (int)(lo / a.M);
+  const double* row = b.p.pack[q] + (lo - (long long)q * a.M) * (a.n + 1);     // local or over NVLink
+  if (a.n == 3) {                                                               // one 32-byte sector
+    const double2 r0 = __ldcg(reinterpret_cast<const double2*>(row));
+    const double r2 = __ldcg(row + 2);
+    a.x_new[j] = r0.x; a.x_new[a.M + j] = r0.y; a.x_new[2 * a.M + j] = r2;
+  } else {
+    for (int i = 0; i < a.n; ++i) a.x_new[i * a.M + j] = __ldcg(row + i);
+  }
+  a.logw[j] = -log((double)a.M_total);
+}
 
 static int fill_weight_args(PfWeightArgs& a, int64_t M, int32_t n, int32_t L, const double* x_dev, const double* y_host,
                             const double* H_host, const double* R_host, double* logw_dev) {
@@ -341,7 +404,7 @@ extern "C" int odeu_pf_normalize(int64_t M, int64_t M_total, int32_t n, int32_t 
     set_error("odeu_pf_normalize: invalid argument");
     return -1;
   }
-  PfNormArgs a = {M, M_total, n, G, triples_dev, x_dev, logw_dev, pack_dev, stats_dev, ess_hist_dev, flag_hist_dev, ess_frac};
+  PfNormArgs a = {M, M_total, n, G, triples_dev, x_dev, logw_dev, pack_dev, stats_dev, ess_hist_dev, flag_hist_dev, ess_frac, nullptr};
   pf_normalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(a);
   count_launch();
   cudaError_t err = cudaGetLastError();
@@ -399,5 +462,73 @@ extern "C" int odeu_pf_scan_resample(int64_t M, int64_t M_total, int64_t slot_lo
   count_launch();
   err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("odeu_pf_scan_resample: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
+// ---- peer-memory entry points (see PfPeers).  Pointer tables are HOST arrays of G device pointers, one per rank,
+// as torch.distributed._symmetric_memory (or cudaIpcOpenMemHandle) hands them out; G <= 16.
+extern "C" int odeu_pf_publish_triple(const double* triple_dev, double* const* peer_triples_host, int32_t rank, int32_t G,
+                                      void* cuda_stream) {
+  using namespace odeu;
+  if (!triple_dev || !peer_triples_host || G <= 0 || G > PF_MAX_PEERS || rank < 0 || rank >= G) {
+    set_error("odeu_pf_publish_triple: invalid argument (G <= 16)");
+    return -1;
+  }
+  PfPublishArgs a;
+  a.triple = triple_dev; a.rank = rank; a.G = G;
+  for (int q = 0; q < PF_MAX_PEERS; ++q) a.dst[q] = q < G ? peer_triples_host[q] : nullptr;
+  pf_publish_triple_kernel<<<1, 3 * PF_MAX_PEERS, 0, (cudaStream_t)cuda_stream>>>(a);
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("odeu_pf_publish_triple: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
+extern "C" int odeu_pf_normalize_w(int64_t M, int64_t M_total, int32_t n, int32_t G, const double* triples_dev,
+                                   const double* x_dev, double* logw_dev, double* pack_dev, double* w_dev,
+                                   double* stats_dev, double* ess_hist_dev, double* flag_hist_dev, double ess_frac,
+                                   void* cuda_stream) {
+  using namespace odeu;
+  if (M <= 0 || M_total < M || n <= 0 || n > 16 || G <= 0 || !triples_dev || !x_dev || !logw_dev || !pack_dev || !w_dev ||
+      !stats_dev) {
+    set_error("odeu_pf_normalize_w: invalid argument");
+    return -1;
+  }
+  PfNormArgs a = {M, M_total, n, G, triples_dev, x_dev, logw_dev, pack_dev, stats_dev, ess_hist_dev, flag_hist_dev, ess_frac, w_dev};
+  pf_normalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(a);
+  count_launch();
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("odeu_pf_normalize_w: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+  return 0;
+}
+
+extern "C" int odeu_pf_scan_resample_peer(int64_t M, int64_t M_total, int64_t slot_lo, int32_t n, int32_t G, double u0,
+                                          const double* stats_dev, const double* const* peer_pack_host,
+                                          const double* const* peer_w_host, const double* x_old_dev, double* x_new_dev,
+                                          double* logw_dev, void* scan_dev, int64_t scan_bytes, void* cuda_stream) {
+  using namespace odeu;
+  if (M <= 0 || M_total != M * G || n <= 0 || n > 16 || G <= 0 || G > PF_MAX_PEERS || !stats_dev || !peer_pack_host ||
+      !peer_w_host || !x_old_dev || !x_new_dev || !logw_dev || !scan_dev || scan_bytes < odeu_pf_scan_bytes(M_total)) {
+    set_error("odeu_pf_scan_resample_peer: invalid argument (M_total = G M, G <= 16, scan scratch: odeu_pf_scan_bytes)");
+    return -1;
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  PfPeers peers;
+  for (int q = 0; q < PF_MAX_PEERS; ++q) {
+    peers.pack[q] = q < G ? peer_pack_host[q] : nullptr;
+    peers.w[q] = q < G ? peer_w_host[q] : nullptr;
+  }
+  double* cdf = (double*)scan_dev;
+  void* tmp = (char*)scan_dev + ((M_total * 8 + 255) / 256) * 256;
+  size_t tmp_bytes = (size_t)scan_bytes - (size_t)((M_total * 8 + 255) / 256) * 256;
+  PeerWeightIt it(thrust::counting_iterator<long long>(0), PeerWeight{peers, (long long)M});
+  cudaError_t err = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, it, cdf, (long long)M_total, st);
+  if (err != cudaSuccess) { set_error("odeu_pf_scan_resample_peer: scan failed: %s", cudaGetErrorString(err)); return (int)err; }
+  count_launch();
+  PfResamplePeerArgs a = {{M, M_total, slot_lo, n, u0, stats_dev, cdf, nullptr, x_new_dev, logw_dev}, x_old_dev, peers};
+  pf_resample_peer_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(a);
+  count_launch();
+  err = cudaGetLastError();
+  if (err != cudaSuccess) { set_error("odeu_pf_scan_resample_peer: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
   return 0;
 }

@@ -105,6 +105,43 @@ def _u0(seed: int, event: int) -> float:
     return float(g.random())
 
 
+_PEER_CACHE: Dict[tuple, dict] = {}
+
+
+def _peer_buffers(dev: torch.device, M: int, n: int, ws: int, rank: int) -> Optional[dict]:
+    """Symmetric (peer-mapped) buffers of this rank for the peer-memory bootstrap path: triples [ws][3], packed
+    rows [M][n + 1], weights [M] in ONE allocation that every rank maps over NVLink
+    (torch.distributed._symmetric_memory); cached per shape.  None when the rendezvous is not available
+    (the caller then uses the NCCL all-gather formulation) or when ODEU_PF_NCCL=1 asks for that path."""
+    import os
+    if os.environ.get("ODEU_PF_NCCL") or ws > 16:
+        return None
+    key = (dev.index, M, n, ws)
+    if key in _PEER_CACHE:
+        return _PEER_CACHE[key]
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        tri_d = 32                                            # doubles reserved for the triples (ws <= 10); 256 bytes
+        while tri_d < 3 * ws:
+            tri_d += 32
+        total = tri_d + M * (n + 1) + M
+        buf = symm_mem.empty((total,), dtype=torch.float64, device=dev)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        ptrs = [int(q) for q in hdl.buffer_ptrs]
+        tab = lambda off: (C.c_void_p * ws)(*[q + 8 * off for q in ptrs])
+        out = {"buf": buf, "hdl": hdl, "triples": buf[:3 * ws].view(ws, 3), "pack": buf[tri_d:tri_d + M * (n + 1)].view(M, n + 1),
+               "w": buf[tri_d + M * (n + 1):], "tri_tab": tab(0), "pack_tab": tab(tri_d), "w_tab": tab(tri_d + M * (n + 1))}
+        torch.cuda.synchronize(dev)
+        hdl.barrier(0, 30000)
+    except Exception as exc:                                   # no peer mapping on this system: NCCL formulation
+        import warnings
+        warnings.warn(f"peer-memory bootstrap path unavailable ({type(exc).__name__}: {exc}); using NCCL all-gathers")
+        out = None
+    _PEER_CACHE[key] = out
+    return out
+
+
 def _u0_stream(seed: int, n_events: int) -> np.ndarray:
     """_u0(seed, k) for k = 0 .. n_events - 1 from ONE generator (constructing a Philox bit generator costs
     ~150 us; event k's block is the k-th block of the stream started at counter 0, bit-identical values)."""
@@ -183,9 +220,13 @@ def _bootstrap_fused(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R,
     xb = torch.empty_like(xa)
     logw = torch.full((M,), -math.log(M_total), **f64)
     triple = torch.zeros(3, **f64)
-    triples = torch.zeros(ws, 3, **f64) if ws > 1 else triple.reshape(1, 3)
-    pack = torch.empty(M, n + 1, **f64)
-    pack_all = pack if ws == 1 else torch.empty(M_total, n + 1, **f64)
+    peer = _peer_buffers(dev, M, n, ws, rank) if ws > 1 else None
+    if peer is not None:
+        triples, pack, pack_all = peer["triples"], peer["pack"], peer["pack"]
+    else:
+        triples = torch.zeros(ws, 3, **f64) if ws > 1 else triple.reshape(1, 3)
+        pack = torch.empty(M, n + 1, **f64)
+        pack_all = pack if ws == 1 else torch.empty(M_total, n + 1, **f64)
     stats = torch.zeros(4, **f64)
     ess_hist = torch.zeros(max(n_obs, 1), **f64)
     flag_hist = torch.zeros(max(n_obs, 1), **f64)
@@ -218,10 +259,22 @@ def _bootstrap_fused(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R,
             yk = np.ascontiguousarray(ysh[k])
             N.check(lib.odeu_pf_weight_reduce(M, n, L, pxb, hp(yk), hp(Hh), hp(Rh), plogw, ptriple, pscratch, st),
                     "odeu_pf_weight_reduce")
+            ess_k, flag_k = C.c_void_p(ess_hist.data_ptr() + 8 * k), C.c_void_p(flag_hist.data_ptr() + 8 * k)
+            if peer is not None:
+                # peer-memory path: triples stored straight into every rank's buffer, rows and weights stay with
+                # their owner and are read over NVLink by whoever needs them; two device-side barriers, no NCCL
+                N.check(lib.odeu_pf_publish_triple(ptriple, peer["tri_tab"], rank, ws, st), "odeu_pf_publish_triple")
+                peer["hdl"].barrier(0, 30000)
+                N.check(lib.odeu_pf_normalize_w(M, M_total, n, ws, ptriples, pxb, plogw, ppack, p(peer["w"]), pstats,
+                                                ess_k, flag_k, float(ess_frac), st), "odeu_pf_normalize_w")
+                peer["hdl"].barrier(0, 30000)
+                N.check(lib.odeu_pf_scan_resample_peer(M, M_total, lo, n, ws, float(u0s[k]), pstats, peer["pack_tab"],
+                                                       peer["w_tab"], pxb, pxa, plogw, pscan, scan_bytes, st),
+                        "odeu_pf_scan_resample_peer")
+                continue
             if ws > 1:
                 dist.all_gather_into_tensor(triples, tri_in)
-            N.check(lib.odeu_pf_normalize(M, M_total, n, ws, ptriples, pxb, plogw, ppack, pstats,
-                                          C.c_void_p(ess_hist.data_ptr() + 8 * k), C.c_void_p(flag_hist.data_ptr() + 8 * k),
+            N.check(lib.odeu_pf_normalize(M, M_total, n, ws, ptriples, pxb, plogw, ppack, pstats, ess_k, flag_k,
                                           float(ess_frac), st), "odeu_pf_normalize")
             if ws > 1:
                 dist.all_gather_into_tensor(pack_all, pack)

@@ -10,7 +10,7 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 plan = Plan(N.ODE_LORENZ, N.SOLVER_RKF45, 0.01)
-M, T, every = 1_000_000, 1000, 10
+M, T, every = (int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000), 1000, 10
 xs = runners.solve_trajectory(plan, [1.0, 1.0, 1.0], T, device=dev)
 ys = xs[every::every] + np.random.default_rng(8).normal(0.0, 0.1, xs[every::every].shape)
 def run(nccl, ess_frac):

@@ -70,9 +70,18 @@ extern "C" {
 
 int odeu_version(void) { return ODEU_VERSION; }
 
-int odeu_plan_create(const odeu_plan_desc* desc, odeu_plan** out) {
-  if (!desc || !out) { set_error("odeu_plan_create: null argument"); return -1; }
+int odeu_plan_create(const odeu_plan_desc* desc_in, odeu_plan** out) {
+  if (!desc_in || !out) { set_error("odeu_plan_create: null argument"); return -1; }
   *out = nullptr;
+  // MultiCompartmentHodgkinHuxley(num_compartments = 1) (hodgkin_huxley.py:284-439 with an empty coupling_coeffs) IS
+  // the single-compartment model: same equations, and its flat parameter layout [C, A, g_Na, ..., V_x] is the
+  // single-compartment order, so the plan is served by the single-compartment kernels
+  odeu_plan_desc mapped = *desc_in;
+  if (mapped.ode_id == ODEU_ODE_MULTI_HH && mapped.num_compartments == 1) {
+    mapped.ode_id = ODEU_ODE_HODGKIN_HUXLEY;
+    mapped.num_compartments = 0;
+  }
+  const odeu_plan_desc* desc = &mapped;
   if (!(desc->step_size > 0.0)) { set_error("odeu_plan_create: step_size must be > 0"); return -1; }
   if (desc->cov_fn_id < ODEU_COV_DIAGONAL || desc->cov_fn_id > ODEU_COV_STATIC_DIAGONAL) {
     set_error("odeu_plan_create: unknown cov_fn_id %d", desc->cov_fn_id);

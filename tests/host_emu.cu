@@ -236,22 +236,24 @@ static int emu_dispatch(const odeu_plan_desc& d, const double* theta_default, in
                         const odeu_ekf_io* e, const odeu_pf_io* pf, const odeu_grad_io* g = nullptr,
                         const odeu_sens_io* s = nullptr) {
   odeu_plan plan;
-  plan.desc = d;
+  odeu_plan_desc dm = d;      // same mapping as odeu_plan_create: one compartment = the single-compartment model
+  if (dm.ode_id == ODEU_ODE_MULTI_HH && dm.num_compartments == 1) { dm.ode_id = ODEU_ODE_HODGKIN_HUXLEY; dm.num_compartments = 0; }
+  plan.desc = dm;
   plan.theta_default.assign(theta_default, theta_default + p);
-  switch (d.ode_id) {
+  switch (dm.ode_id) {
     case ODEU_ODE_LORENZ: return emu_solver<OdeLorenz>(plan, e, pf, g, s);
     case ODEU_ODE_VAN_DER_POL: return emu_solver<OdeVanDerPol>(plan, e, pf, g, s);
     case ODEU_ODE_LOTKA_VOLTERRA: return emu_solver<OdeLotkaVolterra>(plan, e, pf, g, s);
     case ODEU_ODE_PENDULUM: return emu_solver<OdePendulum>(plan, e, pf, g, s);
-    case ODEU_ODE_LCAO: if (d.ode_variant == 2) return emu_solver<OdeLCAO<2>>(plan, e, pf, g, s); break;
+    case ODEU_ODE_LCAO: if (dm.ode_variant == 2) return emu_solver<OdeLCAO<2>>(plan, e, pf, g, s); break;
     case ODEU_ODE_HODGKIN_HUXLEY:
-      if (d.ode_variant == 0) return emu_solver<OdeHodgkinHuxley<0>>(plan, e, pf, g, s);
-      if (d.ode_variant == 1) return emu_solver<OdeHodgkinHuxley<1>>(plan, e, pf, g, s);
-      if (d.ode_variant == 4) return emu_solver<OdeHodgkinHuxley<4>>(plan, e, pf, g, s);
+      if (dm.ode_variant == 0) return emu_solver<OdeHodgkinHuxley<0>>(plan, e, pf, g, s);
+      if (dm.ode_variant == 1) return emu_solver<OdeHodgkinHuxley<1>>(plan, e, pf, g, s);
+      if (dm.ode_variant == 4) return emu_solver<OdeHodgkinHuxley<4>>(plan, e, pf, g, s);
       break;
     case ODEU_ODE_MULTI_HH:
-      if (d.num_compartments == 2 && d.ode_variant == 1) return emu_solver<OdeMultiHH<1, 2>>(plan, e, pf, g, s);
-      if (d.num_compartments == 2 && d.ode_variant == 4) return emu_solver<OdeMultiHH<4, 2>>(plan, e, pf, g, s);
+      if (dm.num_compartments == 2 && dm.ode_variant == 1) return emu_solver<OdeMultiHH<1, 2>>(plan, e, pf, g, s);
+      if (dm.num_compartments == 2 && dm.ode_variant == 4) return emu_solver<OdeMultiHH<4, 2>>(plan, e, pf, g, s);
       break;
   }
   return -2;

@@ -130,3 +130,35 @@ def test_observation_schedule_equals_reference_sync_times():
         assert flags.shape[0] == int(f[f"{tag}_nx"])
         np.testing.assert_array_equal(np.nonzero(flags)[0], f[f"{tag}_x"])
         np.testing.assert_array_equal(ymap[flags], f[f"{tag}_y"])
+
+
+def test_single_compartment_multi_hh_plan_is_the_single_compartment_plan():
+    """odeu_plan_create maps MultiCompartmentHodgkinHuxley(num_compartments = 1) onto the single-compartment model
+    (same equations and flat parameter order, hodgkin_huxley.py:284-439): same state dimension, parameter count and -
+    through the host emulation of the kernel source - the same filter run bit for bit; other compartment counts
+    than 1 and 2 are refused with an error, not served by something else."""
+    import util as U
+    from ode_uncertainty_b200 import Plan, _native as N
+    from ode_uncertainty_b200 import ode as O
+    single = O.HodgkinHuxley(model="reduced-1")
+    multi = O.MultiCompartmentHodgkinHuxley(model="reduced-1", num_compartments=1, coupling_coeffs="[]", C=1.0, A="[8.3e-5]",
+                                            g_Na="[25.0]", E_Na="[53.0]", g_K="[7.0]", E_K="[-107.0]", g_leak="[0.1]",
+                                            E_leak="[-70.0]", V_T="[-60.0]", g_M="[0.01]", tau_max="[4e3]", g_L="[0.01]",
+                                            E_Ca="[120.0]", g_T="[0.01]", V_x="[2.0]")
+    np.testing.assert_array_equal(multi.flat_params(multi.params), single.flat_params(single.params))
+    p1 = Plan(N.ODE_HODGKIN_HUXLEY, N.SOLVER_RKF45, 0.01, ode_variant=1, disable_cov_update=True)
+    pm = Plan(N.ODE_MULTI_HH, N.SOLVER_RKF45, 0.01, ode_variant=1, num_compartments=1, disable_cov_update=True)
+    assert (pm.n, pm.p) == (p1.n, p1.p) == (7, 15)
+    x0 = single.build_initial_value(np.array([[-70.0]]), single.params).reshape(1, -1)
+    np.testing.assert_array_equal(multi.build_initial_value(np.array([[-70.0]]), multi.params).reshape(1, -1), x0)
+    T = 12
+    H = np.zeros((1, 7)); H[0, 0] = 1.0
+    kw = dict(t0=9.9, P0_sqrt=np.eye(7) * 1e-6, Q_sqrt=np.eye(7), gamma_sqrt=1e-2, H=H, R_sqrt=np.eye(1) * 0.3,
+              ys=np.full((T, 1), -65.0), correct_flags=np.ones(T, np.uint8), xy_index_map=np.arange(T, dtype=np.int64),
+              theta_shared=single.flat_params(single.params), minimal=True)
+    a = U.run_ekf("hostemu", p1, x0, T, **kw)
+    b = U.run_ekf("hostemu", pm, x0, T, **kw)
+    for k in ("xT", "PT", "nll"):
+        np.testing.assert_array_equal(a[k], b[k])
+    with pytest.raises(ValueError, match="compartments=3"):
+        Plan(N.ODE_MULTI_HH, N.SOLVER_RKF45, 0.01, ode_variant=1, num_compartments=3)

@@ -172,3 +172,22 @@ def test_solve_trajectory_equals_predict_only_filter_mean():
         ref = r.traj["x"][:, 0, :].cpu().numpy()
         assert xs.shape == ref.shape == (301, plan.n)
         np.testing.assert_allclose(xs, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+
+
+def test_single_compartment_multi_hh_matches_reference_code():
+    """MultiCompartmentHodgkinHuxley(num_compartments = 1) (src/ode/hodgkin_huxley.py:284-439 with an empty
+    coupling_coeffs): the plan is mapped onto the single-compartment kernels (csrc/api.cu).  Right-hand side and
+    initial value against the reference's OWN class (fixture: oracle/make_golden_mhh1.py)."""
+    from ast import literal_eval
+    g = dict(np.load(os.path.join(cases.GOLDEN, "ref_mhh1_rhs.npz")))
+    args = literal_eval(str(g["args"]))
+    dev = torch.device("cuda:0")
+    for model in ("reduced-1", "reduced-4", "full"):
+        b = O.MultiCompartmentHodgkinHuxley(model=model, num_compartments=1, **args)
+        f = b.build()
+        n = g[f"x_{model}"].shape[1]
+        assert b.shape == (1, n)
+        np.testing.assert_allclose(b.build_initial_value(np.array([[-68.0]]), b.params).reshape(-1), g[f"x0_{model}"], rtol=1e-12)
+        for x, t, want in zip(g[f"x_{model}"], g[f"t_{model}"], g[f"f_{model}"]):
+            got = f(float(t), torch.tensor(x).reshape(1, n).to(dev), b.params).cpu().numpy().reshape(-1)
+            np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13)

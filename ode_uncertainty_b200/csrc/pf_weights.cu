@@ -2,6 +2,8 @@
 // has no weights, no correct step and no resampling - src/filters/particle_filter.py:24-118,
 // SURVEY F5 - so this step has no reference oracle; BASELINE config 4 names it).
 //   logw_m += log N(y; H x_m, R) = -0.5 d^T R^-1 d - 0.5 log det(2 pi R),  d = y - H x_m
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -303,6 +305,27 @@ struct PeerWeight {                   // global particle index -> weight, read f
   }
 };
 using PeerWeightIt = thrust::transform_iterator<PeerWeight, thrust::counting_iterator<long long>, double>;
+// weights of all ranks into one local array (rank q's slice pulled from its owner with wide coalesced loads, many in
+// flight per SM: a scan that reads the peers through its input iterator is latency-bound on NVLink, 52 us for 10^6
+// weights over 8 GPUs against ~15 us for pull + local scan)
+struct PfPullArgs {
+  PfPeers p;
+  double* dst;             // [G * M]
+  long long M;
+};
+__global__ void __launch_bounds__(256) pf_pull_weights_kernel(const __grid_constant__ PfPullArgs a) {
+  const int q = blockIdx.y;
+  const double* src = a.p.w[q];
+  double* dst = a.dst + (long long)q * a.M;
+  const long long stride = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (((a.M & 1) == 0) && ((reinterpret_cast<unsigned long long>(src) | reinterpret_cast<unsigned long long>(dst)) & 15ull) == 0) {
+    const long long h = a.M >> 1;
+    for (; i < h; i += stride) reinterpret_cast<double2*>(dst)[i] = __ldcg(reinterpret_cast<const double2*>(src) + i);
+  } else {
+    for (; i < a.M; i += stride) dst[i] = __ldcg(src + i);
+  }
+}
 struct PfResamplePeerArgs {
   PfResampleArgs r;                   // (r.pack unused)
   const double* x_old;
@@ -521,8 +544,20 @@ extern "C" int odeu_pf_scan_resample_peer(int64_t M, int64_t M_total, int64_t sl
   double* cdf = (double*)scan_dev;
   void* tmp = (char*)scan_dev + ((M_total * 8 + 255) / 256) * 256;
   size_t tmp_bytes = (size_t)scan_bytes - (size_t)((M_total * 8 + 255) / 256) * 256;
-  PeerWeightIt it(thrust::counting_iterator<long long>(0), PeerWeight{peers, (long long)M});
-  cudaError_t err = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, it, cdf, (long long)M_total, st);
+  static const bool remote_scan = getenv("ODEU_PF_REMOTE_SCAN") != nullptr;      // A/B switch: scan through the peers
+  cudaError_t err;
+  if (remote_scan) {
+    PeerWeightIt it(thrust::counting_iterator<long long>(0), PeerWeight{peers, (long long)M});
+    err = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, it, cdf, (long long)M_total, st);
+  } else {
+    PfPullArgs pa = {peers, cdf, (long long)M};
+    long long bx = (M / 2 + 255) / 256;
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    pf_pull_weights_kernel<<<dim3((unsigned)bx, (unsigned)G), 256, 0, st>>>(pa);
+    count_launch();
+    err = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, cdf, cdf, (long long)M_total, st);     // in place
+  }
   if (err != cudaSuccess) { set_error("odeu_pf_scan_resample_peer: scan failed: %s", cudaGetErrorString(err)); return (int)err; }
   count_launch();
   PfResamplePeerArgs a = {{M, M_total, slot_lo, n, u0, stats_dev, cdf, nullptr, x_new_dev, logw_dev}, x_old_dev, peers};

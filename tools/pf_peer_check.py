@@ -40,4 +40,11 @@ for ess_frac in (2.0, 0.5):
         print(f"ess_frac={ess_frac}: peer-memory {tp:.2f} ms, NCCL all-gather {tn:.2f} ms, {len(a['resampled'])} resampling events, "
               f"loglik={a['loglik']:.9f}, bit-identical on all ranks: {bool(ok.item())}", flush=True)
     assert bool(ok.item())
+if os.environ.get("PF_PROFILE"):
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize(); dist.barrier()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        run(False, 2.0); torch.cuda.synchronize()
+    if rank == 0:
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=70), flush=True)
 dist.destroy_process_group()

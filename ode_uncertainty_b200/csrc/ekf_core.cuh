@@ -169,6 +169,55 @@ ODEU_HD void rk_step_plain(double t, double h, const double* x, const PT* th,
   }
 }
 
+// Same step, same operation order (so the same bits), with the tableau coefficients read from the kernel arguments:
+// as constant-bank operands of the DFMAs they cost nothing, as compile-time immediates two UMOVs per use (ncu: 40 of
+// the 370 instructions of a Lorenz particle-step).
+template <class Ode, class Tab, class PT>
+ODEU_HD void rk_step_plain_st(double t, double h, const ScaledTableau& st, const double* x, const PT* th,
+                              double* xn, double* eps) {
+  constexpr int n = Ode::NX;
+  constexpr int S = Tab::S;
+  double Ks[S][n];
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    double Xi[n];
+#pragma unroll
+    for (int m = 0; m < n; ++m) {
+      double s = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int j = 0; j < i; ++j) {
+        if (Tab::a(i, j) != 0.0) {
+          if (first) { s = Ks[j][m] * st.a[i][j]; first = false; }
+          else s = fma(st.a[i][j], Ks[j][m], s);
+        }
+      }
+      Xi[m] = first ? x[m] : fma(h, s, x[m]);
+    }
+    Ode::rhs(t + h * Tab::c(i), Xi, th, Ks[i]);
+  }
+#pragma unroll
+  for (int m = 0; m < n; ++m) {
+    double s1 = 0.0, s0 = 0.0;
+    bool f1 = true, f0 = true;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      if (Tab::b(1, j) != 0.0) {
+        if (f1) { s1 = Ks[j][m] * st.b1[j]; f1 = false; }
+        else s1 = fma(st.b1[j], Ks[j][m], s1);
+      }
+      if (Tab::b(0, j) != 0.0) {
+        if (f0) { s0 = Ks[j][m] * st.b0[j]; f0 = false; }
+        else s0 = fma(st.b0[j], Ks[j][m], s0);
+      }
+    }
+    const double x1 = fma(h, s1, x[m]);
+    const double x0 = fma(h, s0, x[m]);
+    xn[m] = x1;
+    eps[m] = fabs(x0 - x1);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // P <- J P J^T (symmetric result; both triangles written so later code can index freely).
 template <int n>

@@ -301,6 +301,7 @@ int launch_pf(const odeu_plan& plan, const odeu_pf_io& io, cudaStream_t stream) 
   constexpr int BLOCK = 128;
   PfArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_pf_args<Ode>(plan, io, a)) return rc;
+  if constexpr (!is_implicit<Tab>::value) fill_scaled_tableau<Tab>(plan.desc.step_size, a.st);
   const long long grid = (io.M + BLOCK - 1) / BLOCK;
   pf_thread_kernel<Ode, Tab, BLOCK><<<(unsigned)grid, BLOCK, 0, stream>>>(a);
   count_launch();

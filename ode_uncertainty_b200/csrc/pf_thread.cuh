@@ -94,6 +94,7 @@ struct PfArgs {
   double* xT; double* epsT; double* tT; double* out_t; double* out_x; double* out_eps;
   double x0s[NX];
   double theta_shared[NP];
+  ScaledTableau st;        // tableau coefficients as constant-bank operands (explicit solvers)
 };
 
 template <class Ode, class Tab>
@@ -126,7 +127,7 @@ ODEU_HD void pf_particle(const PfArgs<Ode::NX, Ode::NP>& a, const long long m) {
       double Jd[n][n];      // (the step Jacobian comes with the Newton solve; unused here)
       dirk_step_generic<Ode, Tab, double>(t, a.h, x, th, xn, eps, Jd);
     } else {
-      rk_step_plain<Ode, Tab>(t, a.h, x, th, xn, eps);
+      rk_step_plain_st<Ode, Tab>(t, a.h, a.st, x, th, xn, eps);
     }
     t = t + a.h;
     if (gid != 0 && !a.noise_free) {

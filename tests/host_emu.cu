@@ -175,6 +175,7 @@ template <class Ode, class Tab>
 int emu_pf(const odeu_plan& plan, const odeu_pf_io& io) {
   PfArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_pf_args<Ode>(plan, io, a)) return rc;
+  if constexpr (!is_implicit<Tab>::value) fill_scaled_tableau<Tab>(plan.desc.step_size, a.st);
   for (long long m = 0; m < io.M; ++m) pf_particle<Ode, Tab>(a, m);
   return 0;
 }

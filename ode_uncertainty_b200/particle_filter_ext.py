@@ -5,12 +5,17 @@ src/filters/particle_filter.py:24-118), so there is no reference orac
 module; BASELINE config 4 names its global steps.  Prediction is the reference-parity kernel
 (`odeu_pf_run`); on top of it
 
-    weights      logw += log N(y; H x, R)                 odeu_pf_weight_update (CUDA)
-    normalise    logw -= logsumexp over ALL ranks          all-reduce(max) + all-reduce(sum)
-    ESS          1 / sum w^2                               all-reduce(sum)
-    resample     systematic, when ESS < ess_frac * M:      all-gather of G partial sums, then one
-                 descendants of a rank's particles occupy  all-to-all of the surviving particles
-                 a contiguous range of global slots
+    weights      logw += log N(y; H x, R), fused with the rank's      odeu_pf_weight_reduce (CUDA)
+                 (max, sum exp, sum exp^2) triple
+    normalise    logw -= logsumexp over ALL ranks, ESS and the        odeu_pf_normalize(_w): device scalars,
+                 resampling decision                                  no host read
+    resample     systematic, every rank resamples its own global      odeu_pf_scan_resample(_peer)
+                 slots from the SAME global CDF
+Between the ranks, per observation: N = 1 nothing; N > 1 over NVLink PEER MEMORY (default: triples stored into every
+rank's symmetric buffer, weights pulled and ancestor rows fetched from their owners, two device-side barriers, no NCCL
+on the data path) or, with ODEU_PF_NCCL=1 / without peer mapping, two NCCL all-gathers (triples; packed rows).  Both give
+the same bits.  `fused=False` keeps the round-1 eager formulation (all-reduces, all-gather of partial sums, all-to-all
+of the surviving particles with host-known split sizes) as the cross-check of the tests.
 
 Particles are sharded by contiguous global slots (`distributed.shard_bounds`); the random stream
 of the prediction is keyed by global slot and step, the resampling offset by (seed, event), so
@@ -108,7 +113,7 @@ def _u0(seed: int, event: int) -> float:
 _PEER_CACHE: Dict[tuple, dict] = {}
 
 
-def _peer_buffers(dev: torch.device, M: int, n: int, ws: int, rank: int) -> Optional[dict]:
+def _peer_buffers(dev: torch.device, M: int, n: int, ws: int) -> Optional[dict]:
     """Symmetric (peer-mapped) buffers of this rank for the peer-memory bootstrap path: triples [ws][3], packed
     rows [M][n + 1], weights [M] in ONE allocation that every rank maps over NVLink
     (torch.distributed._symmetric_memory); cached per shape.  None when the rendezvous is not available
@@ -220,7 +225,7 @@ def _bootstrap_fused(plan: Plan, M_total: int, T: int, ys, obs_every: int, H, R,
     xb = torch.empty_like(xa)
     logw = torch.full((M,), -math.log(M_total), **f64)
     triple = torch.zeros(3, **f64)
-    peer = _peer_buffers(dev, M, n, ws, rank) if ws > 1 else None
+    peer = _peer_buffers(dev, M, n, ws) if ws > 1 else None
     if peer is not None:
         triples, pack, pack_all = peer["triples"], peer["pack"], peer["pack"]
     else:

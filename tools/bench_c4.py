@@ -8,8 +8,8 @@ Diagonal scale 1, particle 0 noise-free.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/bench_c4.py M T [--bootstrap]
 Under torchrun the M particles are SHARDED over the ranks (strong scaling, config 4 is a fixed
 1M-particle ensemble); the random stream is keyed by global particle index, so the ensemble does not
-depend on G.  The bootstrap variant uses NCCL for the global steps only: all-reduce(max, sum) of
-the log-weights, all-gather of the partial sums, all-to-all of the surviving particles.  With solver-error-sized noise the weights stay nearly uniform
+depend on G.  The bootstrap variant's global steps run over NVLink peer memory (or two NCCL all-gathers with
+ODEU_PF_NCCL=1), see particle_filter_ext.py.  With solver-error-sized noise the weights stay nearly uniform
 and the ESS criterion never fires; --force-resample resamples at every observation so the exchange is
 measured."""
 import os

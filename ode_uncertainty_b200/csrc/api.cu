@@ -116,9 +116,9 @@ int odeu_plan_create(const odeu_plan_desc* desc_in, odeu_plan** out) {
     delete p;
     return -2;
   }
-  p->coop_launch = desc->ode_id == ODEU_ODE_HODGKIN_HUXLEY ? resolve_coop_hh(desc->ode_variant, desc->solver_id)
+  p->rows_launch = desc->ode_id == ODEU_ODE_HODGKIN_HUXLEY ? resolve_rows_hh(desc->ode_variant, desc->solver_id)
                    : desc->ode_id == ODEU_ODE_MULTI_HH
-                       ? resolve_coop_multi_hh(desc->ode_variant, desc->num_compartments, desc->solver_id)
+                       ? resolve_rows_multi_hh(desc->ode_variant, desc->num_compartments, desc->solver_id)
                        : nullptr;
   p->ekf_launch = fn.ekf;
   p->pf_launch = fn.pf;
@@ -149,8 +149,8 @@ int64_t odeu_ekf_workspace_bytes(const odeu_plan* plan, int64_t B, int64_t T) {
 int odeu_ekf_run(const odeu_plan* plan, const odeu_ekf_io* io, void* cuda_stream) {
   if (!plan || !io) { set_error("odeu_ekf_run: null argument"); return -1; }
   if (!plan->ekf_launch) { set_error("odeu_ekf_run: this plan is served by odeu_ekf_dense_run"); return -2; }
-  if (plan->coop_launch) {   // medium-size systems: column-parallel cooperative kernel when eligible
-    const int rc = plan->coop_launch(*plan, *io, (cudaStream_t)cuda_stream);
+  if (plan->rows_launch) {   // medium-size systems: row kernel when eligible
+    const int rc = plan->rows_launch(*plan, *io, (cudaStream_t)cuda_stream);
     if (rc != -100) return rc;
   }
   return plan->ekf_launch(*plan, *io, (cudaStream_t)cuda_stream);

@@ -50,7 +50,7 @@ struct GradArgs {
   double* out_t; double* out_x; double* out_eps; double* out_P; double* out_yhat; double* out_S;
   double P0s[NX * NX], GQ[NX * NX], H[NX * NX], R[NX * NX];
   double theta_shared[NP];
-  // run-time copy of the tableau for the rolled stage loops of the cooperative kernel
+  // run-time copy of the tableau (constant-bank operands of the row kernel)
   int rt_S;
   double rt_A[8][8], rt_b[2][8], rt_c[8];
   // stage-tangent schedule of the row-parallel kernel (ekf_rows.cuh): which stage tangents the
@@ -62,53 +62,6 @@ struct GradArgs {
   // each row, valid when h_sel_all != 0
   int h_sel[8], h_sel_all;
 };
-
-// Same step as rk_step_generic with ROLLED stage loops and the tableau read from the kernel
-// arguments: the Hodgkin-Huxley right-hand side is large, and six inlined copies of its dual
-// evaluation overflow the instruction cache (ncu: stall_no_instruction dominated the unrolled
-// cooperative kernel; rolling gave +22 % on C3).  One tangent column (seed e_c0).
-template <class Ode, int ST_MAX, class S, int NXA, int NPA>
-ODEU_HD void rk_step_rolled(const GradArgs<NXA, NPA>& a, double t, const S* x, const S* th, int c0,
-                            S* xn, S* eps, S* Jcol) {
-  constexpr int n = Ode::NX;
-  using D = GDual<S, 1>;
-  const double h = a.h;
-  const int St = a.rt_S;
-  D Ks[ST_MAX][n];
-#pragma unroll 1
-  for (int i = 0; i < St; ++i) {
-    D Xi[n];
-#pragma unroll 1
-    for (int m = 0; m < n; ++m) {
-      D s = D(0.0);
-#pragma unroll 1
-      for (int j = 0; j < i; ++j) {
-        const double aij = a.rt_A[i][j];
-        if (aij != 0.0) s = s + Ks[j][m] * aij;
-      }
-      D X;
-      X.v = x[m];
-      X.d[0] = S((m == c0) ? 1.0 : 0.0);
-      Xi[m] = X + s * h;
-    }
-    Ode::rhs(t + h * a.rt_c[i], Xi, th, Ks[i]);
-  }
-#pragma unroll 1
-  for (int m = 0; m < n; ++m) {
-    D s1 = D(0.0);
-    S s0 = S(0.0);
-#pragma unroll 1
-    for (int j = 0; j < St; ++j) {
-      if (a.rt_b[1][j] != 0.0) s1 = s1 + Ks[j][m] * a.rt_b[1][j];
-      if (a.rt_b[0][j] != 0.0) s0 = s0 + Ks[j][m].v * a.rt_b[0][j];
-    }
-    const S x1 = x[m] + s1.v * h;
-    const S x0 = x[m] + s0 * h;
-    Jcol[m] = S((m == c0) ? 1.0 : 0.0) + s1.d[0] * h;
-    xn[m] = x1;
-    eps[m] = d_abs(x0 - x1);
-  }
-}
 
 // One RK step on scalar type S carrying KC tangent columns c0.. (identity seeds).
 template <class Ode, class Tab, int KC, class S>

@@ -1,4 +1,4 @@
-// Row-parallel cooperative EKF kernel for ODE plugins with a sparse right-hand-side Jacobian
+// Row-parallel EKF kernel (one CTA = a block of trajectories x their rows) for ODE plugins with a sparse right-hand-side Jacobian
 // (the Hodgkin-Huxley family; BASELINE config 3: loss and forward-mode gradient).
 //
 // Same step as everywhere else (predict src/filters/sqrt_ekf.py:92-197 over the RK step
@@ -7,7 +7,7 @@
 //
 //   * thread (trajectory tl, row r) owns equation r of the system: it evaluates f_r at every RK
 //     stage TOGETHER with the non-zero partials d f_r / d x (Ode::row), so each `exp` of the rate
-//     functions is computed once per stage (the column-parallel kernel, ekf_coop.cuh, recomputed
+//     functions is computed once per stage (round 1's column-parallel kernel recomputed
 //     the whole right-hand side in all n column threads);
 //   * the same thread owns tangent COLUMN r of the step Jacobian: the stage tangents follow from
 //     K'_i[:, r] = Df_i * (e_r + h sum_j a_ij K'_j[:, r]) with the SPARSE Df_i read from shared
@@ -28,7 +28,7 @@
 // The per-thread body is a struct with one method per barrier interval, so the identical source
 // is replayed sequentially on the host by the test-only emulation (tests/host_emu.cu).
 #pragma once
-#include "ekf_coop.cuh"
+#include "ekf_grad.cuh"
 #include "vec2.cuh"
 
 namespace odeu {

@@ -1,4 +1,4 @@
-// Gradient / cooperative kernel instantiations: single-compartment Hodgkin-Huxley.
+// Gradient / row kernel instantiations: single-compartment Hodgkin-Huxley.
 #include "launch_grad.cuh"
 namespace odeu {
 GradLaunchFn resolve_grad_hh(int model, int solver) {
@@ -9,10 +9,10 @@ GradLaunchFn resolve_grad_hh(int model, int solver) {
     default: return nullptr;
   }
 }
-CoopLaunchFn resolve_coop_hh(int model, int solver) {
+RowsLaunchFn resolve_rows_hh(int model, int solver) {
   switch (model) {
-    case 0: return resolve_coop_solver<OdeHodgkinHuxley<0>>(solver);
-    case 1: return resolve_coop_solver<OdeHodgkinHuxley<1>>(solver);
+    case 0: return resolve_rows_solver<OdeHodgkinHuxley<0>>(solver);
+    case 1: return resolve_rows_solver<OdeHodgkinHuxley<1>>(solver);
     default: return nullptr;   // reduced-4 (n = 4) stays on the register kernel
   }
 }

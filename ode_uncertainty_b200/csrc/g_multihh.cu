@@ -1,4 +1,4 @@
-// Gradient / cooperative kernel instantiations: 2-compartment Hodgkin-Huxley (BASELINE config 3).
+// Gradient / row kernel instantiations: 2-compartment Hodgkin-Huxley (BASELINE config 3).
 #include "launch_grad.cuh"
 namespace odeu {
 GradLaunchFn resolve_grad_multi_hh(int model, int nc, int solver) {
@@ -9,11 +9,11 @@ GradLaunchFn resolve_grad_multi_hh(int model, int nc, int solver) {
     default: return nullptr;
   }
 }
-CoopLaunchFn resolve_coop_multi_hh(int model, int nc, int solver) {
+RowsLaunchFn resolve_rows_multi_hh(int model, int nc, int solver) {
   if (nc != 2) return nullptr;
   switch (model) {
-    case 1: return resolve_coop_solver<OdeMultiHH<1, 2>>(solver);
-    case 4: return resolve_coop_solver<OdeMultiHH<4, 2>>(solver);
+    case 1: return resolve_rows_solver<OdeMultiHH<1, 2>>(solver);
+    case 4: return resolve_rows_solver<OdeMultiHH<4, 2>>(solver);
     default: return nullptr;
   }
 }

@@ -14,7 +14,7 @@ struct GradCfg {
   static constexpr int BLOCK = 64;
 };
 
-// `g` may be null: NLL-only use of the cooperative kernel (p_opt = 0).
+// `g` may be null: filter-only use of the row kernel (p_opt = 0).
 template <class Ode>
 int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io* gp,
                    GradArgs<Ode::NX, Ode::NP>& a) {
@@ -101,27 +101,6 @@ int fill_grad_args(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad
   return 0;
 }
 
-// Cooperative column-parallel kernel (ekf_coop.cuh) for the medium-size systems.
-template <class Ode>
-constexpr bool coop_eligible_static() { return Ode::NX > 4 && Ode::NX <= 16; }
-template <class Ode>
-bool coop_eligible(const odeu_ekf_io& io) {
-  return coop_eligible_static<Ode>() && 3 * io.L <= Ode::NX && !io.cov_scale_batch && !io.nll_nan_to_num && !io.P0 && io.save_interval == 0 &&
-         !io.skip_predict && !io.epsT && !io.yhatT && !io.ST && !io.tT;
-}
-
-template <class Ode, class Tab, class S, int TB>
-int launch_coop_tb(const GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
-  constexpr int n = Ode::NX;
-  const size_t smem = (size_t)2 * n * n * TB * sizeof(S);
-  auto kern = ekf_coop_kernel<Ode, Tab, S, TB>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("coop kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
-  const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
-  kern<<<(unsigned)((units + TB - 1) / TB), n * TB, smem, stream>>>(a, PT);
-  return 0;
-}
-
 template <class Tab, int NXA, int NPA>
 void fill_rt_tableau(GradArgs<NXA, NPA>& a) {
   a.rt_S = Tab::S;
@@ -200,18 +179,6 @@ int launch_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) 
   }
 }
 
-template <class Ode, class Tab, class S>
-int launch_coop(GradArgs<Ode::NX, Ode::NP>& a, double* PT, cudaStream_t stream) {
-  fill_rt_tableau<Tab>(a);
-  if constexpr (coop_eligible_static<Ode>()) {
-    constexpr int n = Ode::NX;
-    if ((size_t)2 * n * n * 32 * sizeof(S) <= 220 * 1024) return launch_coop_tb<Ode, Tab, S, 32>(a, PT, stream);
-    return launch_coop_tb<Ode, Tab, S, 16>(a, PT, stream);
-  } else {
-    return -2;
-  }
-}
-
 template <class Ode, class Tab>
 int launch_sens(const odeu_plan& plan, const odeu_sens_io& s, cudaStream_t stream) {
   constexpr int NP = Ode::NP;
@@ -247,9 +214,8 @@ int launch_grad(const odeu_plan& plan, const odeu_ekf_io* iop, const odeu_grad_i
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, &g, a)) return rc;
   if constexpr (!is_implicit<Tab>::value)       // (implicit solver plugins: thread-per-unit kernel below)
-  if (rows_eligible<Ode, Tab, GDual<double, 1>>(io) || coop_eligible<Ode>(io)) {
-    if (int rc = rows_eligible<Ode, Tab, GDual<double, 1>>(io) ? launch_rows<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)
-                                        : launch_coop<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)) return rc;
+  if (rows_eligible<Ode, Tab, GDual<double, 1>>(io)) {
+    if (int rc = launch_rows<Ode, Tab, GDual<double, 1>>(a, nullptr, stream)) return rc;
     count_launch();
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("odeu_ekf_grad_run: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
@@ -264,15 +230,14 @@ int launch_grad(const odeu_plan& plan, const odeu_ekf_io* iop, const odeu_grad_i
   return 0;
 }
 
-// NLL-only run of a medium-size system through the cooperative kernel (called by odeu_ekf_run
-// when only nll / xT / PT are requested); returns -100 when the run is not eligible.
+// Filter run of a medium-size system (the Hodgkin-Huxley family) through the row kernel, called by odeu_ekf_run
+// first; returns -100 when the run is not eligible (it then takes the thread-per-trajectory kernel).
 template <class Ode, class Tab>
-int launch_coop_nll(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream) {
-  if (!rows_eligible<Ode, Tab, double>(io) && !coop_eligible<Ode>(io)) return -100;
+int launch_rows_nll(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t stream) {
+  if (!rows_eligible<Ode, Tab, double>(io)) return -100;
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, nullptr, a)) return rc;
-  if (int rc = rows_eligible<Ode, Tab, double>(io) ? launch_rows<Ode, Tab, double>(a, io.PT, stream)
-                                      : launch_coop<Ode, Tab, double>(a, io.PT, stream)) return rc;
+  if (int rc = launch_rows<Ode, Tab, double>(a, io.PT, stream)) return rc;
   count_launch();
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) { set_error("odeu_ekf_run: launch failed: %s", cudaGetErrorString(err)); return (int)err; }
@@ -280,12 +245,12 @@ int launch_coop_nll(const odeu_plan& plan, const odeu_ekf_io& io, cudaStream_t s
 }
 
 template <class Ode>
-CoopLaunchFn resolve_coop_solver(int solver) {
+RowsLaunchFn resolve_rows_solver(int solver) {
   switch (solver) {
-    case ODEU_SOLVER_RKF45: return &launch_coop_nll<Ode, TabRKF45>;
-    case ODEU_SOLVER_DOPRI65: return &launch_coop_nll<Ode, TabDopri65>;
-    case ODEU_SOLVER_BS32: return &launch_coop_nll<Ode, TabBS32>;
-    case ODEU_SOLVER_HEUN_EULER: return &launch_coop_nll<Ode, TabHeunEuler>;
+    case ODEU_SOLVER_RKF45: return &launch_rows_nll<Ode, TabRKF45>;
+    case ODEU_SOLVER_DOPRI65: return &launch_rows_nll<Ode, TabDopri65>;
+    case ODEU_SOLVER_BS32: return &launch_rows_nll<Ode, TabBS32>;
+    case ODEU_SOLVER_HEUN_EULER: return &launch_rows_nll<Ode, TabHeunEuler>;
     default: return nullptr;
   }
 }

@@ -20,7 +20,7 @@ struct odeu_plan {
                     double*, cudaStream_t);
   // gradient run, or (sens != null) the parameter-sensitivity weights of the same ODE x solver
   int (*grad_launch)(const odeu_plan&, const odeu_ekf_io*, const odeu_grad_io*, const odeu_sens_io*, cudaStream_t);
-  int (*coop_launch)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);   // null for small systems
+  int (*rows_launch)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);   // null for small systems
 };
 
 namespace odeu {
@@ -33,9 +33,9 @@ using PfLaunchFn = int (*)(const odeu_plan&, const odeu_pf_io&, cudaStream_t);
 using RhsLaunchFn = int (*)(const odeu_plan&, long long, double, const double*, const double*,
                            const double*, double*, cudaStream_t);
 using GradLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io*, const odeu_grad_io*, const odeu_sens_io*, cudaStream_t);
-using CoopLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);
-CoopLaunchFn resolve_coop_hh(int model, int solver);
-CoopLaunchFn resolve_coop_multi_hh(int model, int nc, int solver);
+using RowsLaunchFn = int (*)(const odeu_plan&, const odeu_ekf_io&, cudaStream_t);
+RowsLaunchFn resolve_rows_hh(int model, int solver);
+RowsLaunchFn resolve_rows_multi_hh(int model, int nc, int solver);
 GradLaunchFn resolve_grad_small(int ode_id, int variant, int solver);
 GradLaunchFn resolve_grad_hh(int model, int solver);
 GradLaunchFn resolve_grad_multi_hh(int model, int nc, int solver);

@@ -189,8 +189,7 @@ def ekf_run(plan: Plan, x0: torch.Tensor, T: int, *, t0: float = 0.0, P0_sqrt=No
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             io.workspace, io.workspace_bytes = _dev(ws), wsb
 
-    # minimal=True requests only nll (+ xT, PT with want_final): lets medium-size systems take
-    # the cooperative column-parallel kernel, which does not produce eps / y_hat / S / t outputs
+    # minimal=True requests only nll (+ xT, PT with want_final): no eps / y_hat / S / t outputs are written
     xT = epsT = PT = yT = ST = None
     nll = torch.zeros(B, **f64)
     tT = None if minimal else torch.zeros(1, **f64)

@@ -18,39 +18,6 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch() {}
 
-// Sequential replay of one launch of ekf_coop_kernel: the CTA's threads are CoopThread objects,
-// each phase is run for every thread before the next one starts (= __syncthreads()).
-template <class Ode, class Tab, class S>
-int emu_coop(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
-  constexpr int n = Ode::NX;
-  fill_rt_tableau<Tab>(a);
-  constexpr int TB = 4;                       // small CTA: more CTAs, ragged tail exercised
-  using Th = CoopThread<Ode, Tab, S, TB>;
-  const long long units = a.B * (a.p_opt > 0 ? a.p_opt : 1);
-  std::vector<S> Asm((size_t)n * n * TB), Bsm((size_t)n * n * TB);
-  std::vector<Th> th((size_t)n * TB);
-  for (long long cta = 0; cta < (units + TB - 1) / TB; ++cta) {
-    for (int k = 0; k < n * TB; ++k) th[k].init(a, cta * TB + k % TB, k % TB, k / TB);
-    for (long long step = 0; step < a.T; ++step) {
-      for (auto& t : th) t.phase_rk(a, Asm.data());
-      for (auto& t : th) t.phase_m(Asm.data(), Bsm.data());
-      for (auto& t : th) t.phase_p(a, Asm.data(), Bsm.data());
-      if (a.has_obs && a.flags[step]) {
-        const long long oi = a.ymap[step];
-        for (auto& t : th) t.phase_pht(a, Bsm.data());
-        for (auto& t : th) {
-          double y[n];
-          for (int l = 0; l < a.L; ++l) y[l] = a.ys_per_traj ? a.ys[(oi * a.L + l) * a.B + t.b] : a.ys[oi * a.L + l];
-          t.phase_gain(a, y, Bsm.data());
-        }
-        for (auto& t : th) t.phase_update(a, Bsm.data());
-      }
-    }
-    for (auto& t : th) t.finish(a, PT);
-  }
-  return 0;
-}
-
 // Sequential replay of one launch of ekf_rows_kernel (same barrier intervals, same order).
 template <class Ode, class Tab, class S>
 int emu_rows(GradArgs<Ode::NX, Ode::NP>& a, double* PT) {
@@ -114,13 +81,6 @@ int emu_ekf(const odeu_plan& plan, const odeu_ekf_io& io) {
       if (getenv("ODEU_ROWS_2WIDE")) return emu_rows<Ode, Tab, V2d>(g, io.PT);       // same routing as launch_rows
     }
     return emu_rows<Ode, Tab, double>(g, io.PT);
-  }
-  if constexpr (coop_eligible_static<Ode>() && !is_implicit<Tab>::value) {
-    if (coop_eligible<Ode>(io)) {           // same routing as odeu_ekf_run
-      GradArgs<Ode::NX, Ode::NP> g;
-      if (int rc = fill_grad_args<Ode>(plan, io, nullptr, g)) return rc;
-      return emu_coop<Ode, Tab, double>(g, io.PT);
-    }
   }
   EkfArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_ekf_args<Ode>(plan, io, a)) return rc;
@@ -268,9 +228,6 @@ int emu_grad(const odeu_plan& plan, const odeu_ekf_io& io, const odeu_grad_io& g
   GradArgs<Ode::NX, Ode::NP> a;
   if (int rc = fill_grad_args<Ode>(plan, io, &g, a)) return rc;
   if (rows_eligible<Ode, Tab, GDual<double, 1>>(io)) return emu_rows<Ode, Tab, GDual<double, 1>>(a, nullptr);
-  if constexpr (coop_eligible_static<Ode>() && !is_implicit<Tab>::value) {
-    if (coop_eligible<Ode>(io)) return emu_coop<Ode, Tab, GDual<double, 1>>(a, nullptr);
-  }
   using Cfg = GradCfg<Ode>;
   const int nchunks = (g.p_opt + Cfg::PC - 1) / Cfg::PC;
   for (int c = 0; c < nchunks; ++c)

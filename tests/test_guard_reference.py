@@ -141,7 +141,7 @@ def test_factor_form_resume_is_bitwise():
 
 
 def test_reference_guard_rejected_where_not_served():
-    """n > 4 plans (row / cooperative / thread kernels of the Hodgkin-Huxley family) keep the intended
+    """n > 4 plans (row / thread kernels of the Hodgkin-Huxley family) keep the intended
     guard; asking them for the factor form is an error, not a silent downgrade."""
     spec = cases.CASES["hh_r4_rkf45_temper"]
     out, _ = _run("hostemu", spec, "intended")

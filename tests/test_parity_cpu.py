@@ -155,10 +155,9 @@ def test_time_segmented_run_is_bitwise_identical(name):
 
 
 @pytest.mark.parametrize("name", ["hh_r1_rkf45_temper", "hh_full_rkf45_small_h", "c3_mhh_r1_rkf45_temper"])
-def test_cooperative_kernel_source_matches_oracle_and_thread_kernel(name):
-    """Medium-size systems: the column-parallel cooperative kernel (ekf_coop.cuh, taken when only
-    nll / xT / PT are requested) against the oracle's final state and the thread-per-trajectory
-    kernel, on a ragged batch of perturbed initial conditions."""
+def test_row_kernel_minimal_and_full_output_runs_match_oracle(name):
+    """Medium-size systems (row kernel, ekf_rows.cuh): the run that requests only nll / xT / PT against the run with
+    the full output contract and against the oracle's final state, on a ragged batch of perturbed initial conditions."""
     import util as U
     spec = cases.CASES[name]
     gold = cases.load_golden(name)

@@ -152,7 +152,7 @@ def test_dynamic_scheduler_equals_static_launch_bitwise():
 
 
 @pytest.mark.parametrize("name", ["hh_r1_rkf45_temper", "hh_full_rkf45_small_h", "c3_mhh_r1_rkf45_temper"])
-def test_cooperative_kernel_on_gpu(name):
+def test_row_kernel_minimal_and_full_output_runs_on_gpu(name):
     spec = cases.CASES[name]
     gold = cases.load_golden(name)
     m = cases.materialize(spec)

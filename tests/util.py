@@ -152,7 +152,7 @@ def run_ekf(backend, plan, x0, T, *, t0=0.0, P0_sqrt=None, P0=None, theta=None, 
     PsT, gcount = np.zeros((n * n, B)), np.zeros((2, B), dtype=np.int64)
     if guard != "intended":
         io.PT_sqrt, io.guard_counts = _p(PsT), _p(gcount)
-    if minimal:      # only nll, xT, PT requested (lets medium systems take the cooperative kernel)
+    if minimal:      # only nll, xT, PT requested
         io.xT, io.PT, io.nll = map(_p, (xT, PT, nll))
     else:
         io.xT, io.epsT, io.PT, io.yhatT, io.ST, io.nll, io.tT = map(_p, (xT, epsT, PT, yT, ST, nll, tT))

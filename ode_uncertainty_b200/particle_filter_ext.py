@@ -19,7 +19,7 @@ of the surviving particles with host-known split sizes) as the cross-check of th
 
 Particles are sharded by contiguous global slots (`distributed.shard_bounds`); the random stream
 of the prediction is keyed by global slot and step, the resampling offset by (seed, event), so
-results do not depend on the number of ranks.
+results do not depend on the number of ranks (up to the rounding of the log-sum-exp reduction order).
 """
 from __future__ import annotations
 
